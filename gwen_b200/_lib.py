@@ -1,0 +1,117 @@
+"""ctypes binding of ``libgwen_b200.so`` (C ABI declared in ``include/gwen_b200.h``).
+
+The shared library is the product; this module only loads it, declares the prototypes and
+turns negative return codes into ``RuntimeError``.  There is no CPU fallback: if the library
+is missing the import of :mod:`gwen_b200` fails with instructions to build it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "linear.cu", "linear_tc.cu"]
+
+GWEN_F32, GWEN_BF16 = 0, 1
+GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4
+EPI_NONE, EPI_RELU = 0, 1
+
+
+def nvcc_command(out_path: str = LIB_PATH) -> list:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+            "-I" + os.path.join(_ROOT, "include"), "-o", out_path] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+        [os.path.join(_ROOT, "include", "gwen_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into ``gwen_b200/libgwen_b200.so`` (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = nvcc_command(tmp)
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+class TilePlanStruct(C.Structure):
+    _fields_ = [("num_tiles", C.c_int32), ("max_tile_src", C.c_int32), ("n_dst", C.c_int64),
+                ("order", C.c_void_p), ("tile_ptr", C.c_void_p), ("tsrc_ptr", C.c_void_p),
+                ("tsrc", C.c_void_p), ("msg", C.c_void_p)]
+
+
+_p, _i64, _i32, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/gwen_b200.h declares.
+PROTOTYPES = {
+    "gwen_version": (_int, []),
+    "gwen_last_error": (C.c_char_p, []),
+    "gwen_graph_workspace_bytes": (_int, [_i64, _i64, _u32, C.POINTER(_sz)]),
+    "gwen_graph_build": (_int, [_p, _i64, _i64, _u32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gwen_grid_edge_count": (_i64, [_i64, _i64]),
+    "gwen_grid_edges": (_int, [_i64, _i64, _p, _p]),
+    "gwen_complete_edges": (_int, [_i64, _p, _p]),
+    "gwen_aggregate_fwd": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
+                                  _i64, _i64, _int, _p, _int, _p]),
+    "gwen_tile_plan_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
+    "gwen_tile_plan_build": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p,
+                                    _sz, _p]),
+    "gwen_uniform_tiles": (_int, [_i64, _i32, _p, _p]),
+    "gwen_grid_tiles": (_int, [_i64, _i64, _i32, _i32, _p, _p, _p]),
+    "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _p, _i64, _i64, _i64,
+                                        _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _p]),
+    "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
+    "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+    "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,
+                                      _sz, _p]),
+    "gwen_linear_bwd_weight_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
+    "gwen_relu_bwd": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _p]),
+    "gwen_bias_grad": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _sz, _p]),
+    "gwen_bias_grad_workspace_bytes": (_int, [_i64, _i64, C.POINTER(_sz)]),
+    "gwen_rows_gather": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+    "gwen_rows_scatter": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "gwen_b200: %s is missing -- build it with `python -c \"import __graft_entry__ as g; "
+                "g.build()\"` (nvcc, sm_100a). There is no CPU or PyTorch fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().gwen_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))

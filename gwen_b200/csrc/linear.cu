@@ -1,0 +1,384 @@
+// K2 (CUDA-core path): dense projections y = x W^T (+bias, relu) and the two backward GEMMs, as a
+// register-blocked FFMA GEMM with exact fp32 accumulation.  This is the path for fp32 (the
+// reference runs fp32 Linear on SIMT cuBLAS: allow_tf32 defaults to False) and for shapes the
+// tcgen05 kernel in linear_tc.cu does not take (ragged K, tiny M).  bf16 problems with
+// tensor-core-friendly shapes are routed to linear_tc.cu by gwen_linear_fwd.
+//
+// One kernel serves forward, dgrad and wgrad through operand layout flags:
+//   C[i, j] = sum_r A(i, r) * B(j, r)
+//   A_RMAJOR: A(i, r) = A[i*lda + r]  (reduction index contiguous)   else A[r*lda + i]
+//   B_RMAJOR: B(j, r) = B[j*ldb + r]                                  else B[r*ldb + j]
+//   forward: A = x  (R-major), B = W  (R-major), reduce over K
+//   dgrad  : A = dy (R-major), B = W  (col-major in r = n: B[r*ldw + j]), reduce over N_out
+//   wgrad  : A = dy (A[r*lddy + i]), B = x (B[r*ldx + j]), reduce over M, split across CTAs
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace gwen {
+
+// linear_tc.cu
+int linear_tc_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                        const void* x, const void* w, const void* y);
+int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
+                       int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
+                       cudaStream_t st);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
+constexpr int kGemmThreads = 256;
+
+struct GemmArgs {
+  const void* a;
+  const void* b;
+  void* c;         // T (or float when OUT_F32)
+  const float* bias;
+  int64_t m, n, r;  // C is m x n, reduction length r
+  int64_t lda, ldb, ldc;
+  int64_t r_per_split;  // reduction slice per blockIdx.z
+  int64_t c_split_stride;
+  int relu;
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, int64_t stride, int valid, bool vec, float* f) {
+  // 4 consecutive (stride 1) elements starting at p, `valid` of them in range.
+  if (vec && valid == 4) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+      f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    } else {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+      f[0] = __uint_as_float(v.x << 16);
+      f[1] = __uint_as_float(v.x & 0xffff0000u);
+      f[2] = __uint_as_float(v.y << 16);
+      f[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = i < valid ? to_f32(p[i * stride]) : 0.0f;
+  }
+}
+
+// Stage one operand tile (128 outer x 16 reduction) into registers.  RMAJOR: each thread reads
+// 2 x 4 elements along r; otherwise 2 x 4 elements along the outer index.
+template <typename T, bool RMAJOR>
+__device__ __forceinline__ void fetch_tile(const T* base, int64_t ld, int64_t outer0,
+                                           int64_t outer_n, int64_t r0, int64_t r_end, bool vec,
+                                           float (&reg)[2][4]) {
+  const int tid = threadIdx.x;
+  if constexpr (RMAJOR) {
+    const int rq = (tid & 3) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t o = outer0 + (tid >> 2) + h * 64;
+      const int64_t r = r0 + rq;
+      int valid = o < outer_n ? static_cast<int>(max(int64_t(0), min(int64_t(4), r_end - r))) : 0;
+      load4<T>(base + o * ld + r, 1, valid, vec, reg[h]);
+    }
+  } else {
+    const int oq = (tid & 31) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t r = r0 + (tid >> 5) + h * 8;
+      const int64_t o = outer0 + oq;
+      int valid = r < r_end ? static_cast<int>(max(int64_t(0), min(int64_t(4), outer_n - o))) : 0;
+      load4<T>(base + r * ld + o, 1, valid, vec, reg[h]);
+    }
+  }
+}
+
+template <bool RMAJOR>
+__device__ __forceinline__ void stash_tile(float (*s)[BM + 4], const float (&reg)[2][4]) {
+  const int tid = threadIdx.x;
+  if constexpr (RMAJOR) {
+    const int rq = (tid & 3) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = (tid >> 2) + h * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[rq + i][o] = reg[h][i];
+    }
+  } else {
+    const int oq = (tid & 31) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (tid >> 5) + h * 8;
+      *reinterpret_cast<float4*>(&s[r][oq]) = make_float4(reg[h][0], reg[h][1], reg[h][2], reg[h][3]);
+    }
+  }
+}
+
+template <typename T, bool A_RMAJOR, bool B_RMAJOR, bool OUT_F32>
+__global__ void __launch_bounds__(kGemmThreads) k_gemm(GemmArgs g, bool vec_a, bool vec_b) {
+  __shared__ __align__(16) float sa[2][BK][BM + 4];
+  __shared__ __align__(16) float sb[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  // 1-D tile index, N tiles fastest: CTAs that run together share the A tile through L2.
+  const int64_t n_tiles = (g.n + BN - 1) / BN;
+  const int64_t m0 = (int64_t(blockIdx.x) / n_tiles) * BM, n0 = (int64_t(blockIdx.x) % n_tiles) * BN;
+  const int64_t r_beg = int64_t(blockIdx.y) * g.r_per_split;
+  const int64_t r_end = min(g.r, r_beg + g.r_per_split);
+  const T* A = static_cast<const T*>(g.a);
+  const T* B = static_cast<const T*>(g.b);
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  float ra[2][4], rb[2][4];
+  fetch_tile<T, A_RMAJOR>(A, g.lda, m0, g.m, r_beg, r_end, vec_a, ra);
+  fetch_tile<T, B_RMAJOR>(B, g.ldb, n0, g.n, r_beg, r_end, vec_b, rb);
+  stash_tile<A_RMAJOR>(sa[0], ra);
+  stash_tile<B_RMAJOR>(sb[0], rb);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t r0 = r_beg; r0 < r_end; r0 += BK) {
+    const bool more = r0 + BK < r_end;
+    if (more) {
+      fetch_tile<T, A_RMAJOR>(A, g.lda, m0, g.m, r0 + BK, r_end, vec_a, ra);
+      fetch_tile<T, B_RMAJOR>(B, g.ldb, n0, g.n, r0 + BK, r_end, vec_b, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&sa[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sb[buf][kk][64 + tx * 4]);
+      const float av[TM] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[TN] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash_tile<A_RMAJOR>(sa[buf ^ 1], ra);
+      stash_tile<B_RMAJOR>(sb[buf ^ 1], rb);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  // epilogue
+  using OutT = typename std::conditional<OUT_F32, float, T>::type;
+  OutT* C = static_cast<OutT*>(g.c) + int64_t(blockIdx.y) * g.c_split_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= g.m) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= g.n) continue;
+      float v = acc[i][j];
+      if (g.bias) v += __ldg(g.bias + n);
+      if (g.relu) v = fmaxf(v, 0.0f);
+      if constexpr (OUT_F32) C[m * g.ldc + n] = v; else C[m * g.ldc + n] = from_f32<T>(v);
+    }
+  }
+}
+
+template <typename T>
+bool vec_ok(const void* p, int64_t ld) {
+  const int a = sizeof(T) == 4 ? 16 : 8;
+  return (reinterpret_cast<uintptr_t>(p) % a) == 0 && ld % 4 == 0;
+}
+
+template <typename T, bool AR, bool BR, bool OUT_F32>
+int launch_gemm(const GemmArgs& g, int splits, cudaStream_t st) {
+  const int64_t tiles = ceil_div(g.n, BN) * ceil_div(g.m, BM);
+  if (tiles > INT32_MAX || splits > 65535) return set_err(GWEN_E_NOSUPPORT, "GEMM grid too large");
+  dim3 grid(static_cast<unsigned>(tiles), static_cast<unsigned>(splits));
+  k_gemm<T, AR, BR, OUT_F32><<<grid, kGemmThreads, 0, st>>>(g, vec_ok<T>(g.a, g.lda),
+                                                            vec_ok<T>(g.b, g.ldb));
+  GWEN_LAUNCH_CHECK("k_gemm");
+  return GWEN_OK;
+}
+
+// fixed-order reduction of wgrad split partials: out[i] = sum_s part[s][i], s ascending
+__global__ void k_reduce_splits(const float* __restrict__ part, int splits, int64_t n_elems,
+                                int64_t stride, float* __restrict__ out, int64_t ld_out,
+                                int64_t cols) {
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n_elems) return;
+  float s = 0.0f;
+  for (int k = 0; k < splits; ++k) s += part[k * stride + i];
+  out[(i / cols) * ld_out + (i % cols)] = s;
+}
+
+int wgrad_splits(int64_t m, int64_t k, int64_t n_out) {
+  const int64_t tiles = ceil_div(n_out, BM) * ceil_div(k, BN);
+  int64_t s = ceil_div(int64_t(sm_count()) * 2, tiles);
+  s = std::min<int64_t>(s, ceil_div(m, 4 * BK));
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(s, 512)));
+}
+
+template <typename T>
+__global__ void k_relu_bwd(const T* __restrict__ y, T* __restrict__ dy, int64_t rows, int64_t feat,
+                           int64_t ldy, int64_t lddy) {
+  const int64_t total = rows * feat;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / feat, c = i % feat;
+    if (!(to_f32(y[r * ldy + c]) > 0.0f)) dy[r * lddy + c] = from_f32<T>(0.0f);
+  }
+}
+
+// db partials: block (bx, by) sums rows [by*chunk, (by+1)*chunk) of columns bx*32..+31 in a fixed
+// order: 8 row-lanes stride the chunk sequentially, then a fixed 8-way tree in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) k_bias_partial(const T* __restrict__ dy, int64_t rows,
+                                                      int64_t feat, int64_t lddy, int64_t chunk,
+                                                      float* __restrict__ part) {
+  __shared__ float s[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t c = int64_t(blockIdx.x) * 32 + cx;
+  const int64_t r0 = int64_t(blockIdx.y) * chunk, r1 = min(rows, r0 + chunk);
+  float acc = 0.0f;
+  if (c < feat)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += to_f32(dy[r * lddy + c]);
+  s[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < feat) {
+    float t = ((s[0][cx] + s[1][cx]) + (s[2][cx] + s[3][cx])) +
+              ((s[4][cx] + s[5][cx]) + (s[6][cx] + s[7][cx]));
+    part[int64_t(blockIdx.y) * feat + c] = t;
+  }
+}
+
+constexpr int64_t kBiasChunk = 2048;
+
+}  // namespace
+}  // namespace gwen
+
+using namespace gwen;
+
+static int check_dtype(int dtype) {
+  if (dtype == GWEN_F32 || dtype == GWEN_BF16) return GWEN_OK;
+  return set_err(GWEN_E_DTYPE, "unknown dtype %d", dtype);
+}
+
+extern "C" int gwen_linear_fwd(const void* x, const void* weight, void* y, int64_t m, int64_t k,
+                               int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int dtype,
+                               const float* bias, int epilogue, void* stream) {
+  GWEN_CHECK_ARG(m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (m == 0 || n_out == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(x && weight && y, "null pointer");
+  GWEN_CHECK_ARG(ldx >= k && ldw >= k && ldy >= n_out, "row pitch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int relu = (epilogue & GWEN_EPI_RELU) ? 1 : 0;
+  if (dtype == GWEN_BF16 && linear_tc_supported(m, k, n_out, ldx, ldw, ldy, x, weight, y))
+    return linear_tc_fwd_bf16(x, weight, y, m, k, n_out, ldx, ldw, ldy, bias, relu, st);
+  GemmArgs g{x, weight, y, bias, m, n_out, k, ldx, ldw, ldy, k, 0, relu};
+  return dtype == GWEN_F32 ? launch_gemm<float, true, true, false>(g, 1, st)
+                           : launch_gemm<__nv_bfloat16, true, true, false>(g, 1, st);
+}
+
+extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m,
+                                    int64_t k, int64_t n_out, int64_t lddy, int64_t ldw,
+                                    int64_t lddx, int dtype, void* stream) {
+  GWEN_CHECK_ARG(m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (m == 0 || k == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(dy && weight && dx, "null pointer");
+  GWEN_CHECK_ARG(lddy >= n_out && ldw >= k && lddx >= k, "row pitch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // dx[m, kk] = sum_n dy[m, n] * W[n, kk]:  A = dy (R-major), B(j=kk, r=n) = W[r*ldw + j]
+  GemmArgs g{dy, weight, dx, nullptr, m, k, n_out, lddy, ldw, lddx, n_out, 0, 0};
+  return dtype == GWEN_F32 ? launch_gemm<float, true, false, false>(g, 1, st)
+                           : launch_gemm<__nv_bfloat16, true, false, false>(g, 1, st);
+}
+
+extern "C" int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int64_t n_out,
+                                                      size_t* out) {
+  GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
+  *out = static_cast<size_t>(wgrad_splits(m, k, n_out)) * n_out * k * sizeof(float) + 256;
+  return GWEN_OK;
+}
+
+extern "C" int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t m,
+                                      int64_t k, int64_t n_out, int64_t lddy, int64_t ldx,
+                                      int64_t lddw, int dtype, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  GWEN_CHECK_ARG(m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (k == 0 || n_out == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(dw && ws, "null pointer");
+  GWEN_CHECK_ARG(m == 0 || (dy && x), "null pointer");
+  GWEN_CHECK_ARG(lddy >= n_out && ldx >= k && lddw >= k, "row pitch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int splits = wgrad_splits(m, k, n_out);
+  const size_t need = static_cast<size_t>(splits) * n_out * k * sizeof(float);
+  if (ws_bytes < need) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
+  // dw[n, kk] = sum_m dy[m, n] * x[m, kk]:  A(i=n, r=m) = dy[r*lddy + i], B(j=kk, r=m) = x[r*ldx + j]
+  int64_t per = ceil_div(ceil_div(m, splits), BK) * BK;
+  if (per == 0) per = BK;
+  GemmArgs g{dy, x, ws, nullptr, n_out, k, m, lddy, ldx, k, per, n_out * k, 0};
+  int rc = dtype == GWEN_F32 ? launch_gemm<float, false, false, true>(g, splits, st)
+                             : launch_gemm<__nv_bfloat16, false, false, true>(g, splits, st);
+  if (rc != GWEN_OK) return rc;
+  const int64_t n_elems = n_out * k;
+  k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(
+      static_cast<const float*>(ws), splits, n_elems, n_elems, dw, lddw, k);
+  GWEN_LAUNCH_CHECK("k_reduce_splits");
+  return GWEN_OK;
+}
+
+extern "C" int gwen_relu_bwd(const void* y, void* dy, int64_t rows, int64_t feat, int64_t ldy,
+                             int64_t lddy, int dtype, void* stream) {
+  GWEN_CHECK_ARG(rows >= 0 && feat >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (rows * feat == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(y && dy, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks =
+      static_cast<unsigned>(std::min<int64_t>(ceil_div(rows * feat, 256), int64_t(sm_count()) * 16));
+  if (dtype == GWEN_F32)
+    k_relu_bwd<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(y),
+                                              static_cast<float*>(dy), rows, feat, ldy, lddy);
+  else
+    k_relu_bwd<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y),
+                                                      static_cast<__nv_bfloat16*>(dy), rows, feat,
+                                                      ldy, lddy);
+  GWEN_LAUNCH_CHECK("k_relu_bwd");
+  return GWEN_OK;
+}
+
+extern "C" int gwen_bias_grad_workspace_bytes(int64_t rows, int64_t feat, size_t* out) {
+  GWEN_CHECK_ARG(out && rows >= 0 && feat >= 0, "bad arguments");
+  *out = static_cast<size_t>(std::max<int64_t>(1, ceil_div(rows, kBiasChunk))) * feat *
+             sizeof(float) + 256;
+  return GWEN_OK;
+}
+
+extern "C" int gwen_bias_grad(const void* dy, float* db, int64_t rows, int64_t feat, int64_t lddy,
+                              int dtype, void* ws, size_t ws_bytes, void* stream) {
+  GWEN_CHECK_ARG(rows >= 0 && feat >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (feat == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(db && ws && (rows == 0 || dy), "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunks = std::max<int64_t>(1, ceil_div(rows, kBiasChunk));
+  const size_t need = static_cast<size_t>(chunks) * feat * sizeof(float);
+  if (ws_bytes < need) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
+  if (chunks > 65535) return set_err(GWEN_E_NOSUPPORT, "too many rows for bias_grad");
+  dim3 grid(static_cast<unsigned>(ceil_div(feat, 32)), static_cast<unsigned>(chunks));
+  float* part = static_cast<float*>(ws);
+  if (dtype == GWEN_F32)
+    k_bias_partial<float><<<grid, 256, 0, st>>>(static_cast<const float*>(dy), rows, feat, lddy,
+                                                kBiasChunk, part);
+  else
+    k_bias_partial<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                        rows, feat, lddy, kBiasChunk, part);
+  GWEN_LAUNCH_CHECK("k_bias_partial");
+  k_reduce_splits<<<static_cast<unsigned>(ceil_div(feat, 256)), 256, 0, st>>>(
+      part, static_cast<int>(chunks), feat, feat, db, feat, feat);
+  GWEN_LAUNCH_CHECK("k_reduce_splits");
+  return GWEN_OK;
+}

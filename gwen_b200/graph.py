@@ -1,0 +1,282 @@
+"""Graph side of the hot path: edge-list builders, the one-time CSR preprocessor (K0) and tile plans.
+
+Host-side mirror of what PyG does inside ``GCNConv.forward`` before the arithmetic starts
+(``gcn_norm`` / ``add_remaining_self_loops``; reference call sites ``src/gwen/models_gnn.py:147-149,
+204-206``) and of the graph builder the reference dataset uses (``erdos_renyi_graph(N, 1)`` at
+``src/gwen/utils.py:176``).  All work happens in ``libgwen_b200.so`` on the GPU; tensors are only
+used to own device memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+__all__ = ["GraphCSR", "build_graph", "get_graph", "clear_graph_cache", "grid", "grid_edge_count",
+           "erdos_renyi_graph", "complete_graph", "TilePlan"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("gwen_b200: %s must be a CUDA tensor (there is no CPU fallback)" % name)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# builders
+# ---------------------------------------------------------------------------------------------
+def grid_edge_count(height: int, width: int) -> int:
+    return int(lib().gwen_grid_edge_count(height, width))
+
+
+def grid(height: int, width: int, device="cuda") -> torch.Tensor:
+    """``torch_geometric.utils.grid(height, width)`` edge_index (8-neighbour mesh + self loops,
+    sorted by (row, col)), generated on the device.  SURVEY.md Appendix B.2."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("gwen_b200.grid builds on a CUDA device only")
+    e = grid_edge_count(height, width)
+    with torch.cuda.device(device):
+        out = torch.empty((2, e), dtype=torch.int64, device=device)
+        check(lib().gwen_grid_edges(height, width, out.data_ptr(), _stream()), "gwen_grid_edges")
+    return out
+
+
+def complete_graph(num_nodes: int, device="cuda") -> torch.Tensor:
+    """All ordered pairs (i, j), i != j, sorted by (row, col): the value of
+    ``erdos_renyi_graph(N, edge_prob=1)``."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("gwen_b200.complete_graph builds on a CUDA device only")
+    with torch.cuda.device(device):
+        out = torch.empty((2, num_nodes * (num_nodes - 1)), dtype=torch.int64, device=device)
+        check(lib().gwen_complete_edges(num_nodes, _ptr(out), _stream()), "gwen_complete_edges")
+    return out
+
+
+def erdos_renyi_graph(num_nodes: int, edge_prob: float, directed: bool = False,
+                      device="cuda") -> torch.Tensor:
+    """Drop-in for the call at reference ``src/gwen/utils.py:176``.  Only ``edge_prob >= 1`` (the
+    value GWEN uses) is served; like PyG it draws ``N(N-1)/2`` numbers from the global CPU RNG so
+    that a seeded script initialises its weights identically afterwards."""
+    if edge_prob < 1.0 or directed:
+        raise NotImplementedError("gwen_b200.erdos_renyi_graph serves edge_prob=1, undirected "
+                                  "(the only form the reference calls)")
+    torch.rand(num_nodes * (num_nodes - 1) // 2)  # RNG side effect of the reference builder
+    return complete_graph(num_nodes, device)
+
+
+# ---------------------------------------------------------------------------------------------
+# CSR handle
+# ---------------------------------------------------------------------------------------------
+class TilePlan:
+    """Device arrays of a tile plan + the host struct handed to gwen_aggregate_tiled_fwd."""
+
+    def __init__(self, order, tile_ptr, tsrc_ptr, tsrc, msg, n_dst, max_tile_src, total_src):
+        self.order, self.tile_ptr, self.tsrc_ptr, self.tsrc, self.msg = order, tile_ptr, tsrc_ptr, tsrc, msg
+        self.num_tiles = tile_ptr.numel() - 1
+        self.n_dst, self.max_tile_src, self.total_src = n_dst, max_tile_src, total_src
+        self.struct = _lib.TilePlanStruct(self.num_tiles, max_tile_src, n_dst, _ptr(order),
+                                          _ptr(tile_ptr), _ptr(tsrc_ptr), _ptr(tsrc), _ptr(msg))
+
+
+class GraphCSR:
+    """Destination-sorted CSR of ``edge_index'`` (after self-loop normalisation) with GCN weights.
+
+    ``rowptr int32[N+1]``, ``src int32[E']``, ``w fp32[E']``, ``dis fp32[N]``, ``perm int64[E']``.
+    ``n_src`` may exceed ``n_dst`` for a partition-local graph (owned rows + halo rows).
+    """
+
+    def __init__(self, rowptr, src, w, dis, perm, n_dst, n_src, num_messages, flags,
+                 edge_index=None, grid_shape=None):
+        self.rowptr, self.src, self.w, self.dis, self.perm = rowptr, src, w, dis, perm
+        self.n_dst, self.n_src, self.num_messages, self.flags = n_dst, n_src, num_messages, flags
+        self.edge_index = edge_index
+        self.grid_shape = grid_shape
+        self._transposed: Optional["GraphCSR"] = None
+        self._plans: Dict[Tuple, TilePlan] = {}
+        self.order: Optional[torch.Tensor] = None  # locality order for the row kernel
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    # -- backward graph ----------------------------------------------------------------------
+    def transposed(self) -> "GraphCSR":
+        """CSR of the transposed graph with the SAME per-edge weights (Appendix A.7)."""
+        if self._transposed is None:
+            if self.edge_index is None:
+                raise RuntimeError("transposed graph needs the original edge_index")
+            self._transposed = _build(self.edge_index, self.n_dst, self.flags | _lib.GRAPH_TRANSPOSE,
+                                      dis_in=self.dis)
+            self._transposed.grid_shape = self.grid_shape
+        return self._transposed
+
+    # -- tile plans ----------------------------------------------------------------------------
+    def tile_plan(self, tile: Optional[Tuple[int, ...]] = None) -> TilePlan:
+        """``tile=(th, tw)`` -> 2-D blocks of the grid (needs ``grid_shape``); ``tile=(rows,)`` ->
+        contiguous destination ranges.  Default: (8, 32) blocks on a grid, else 128-row ranges."""
+        if tile is None:
+            tile = (8, 32) if self.grid_shape is not None else (128,)
+        tile = tuple(int(t) for t in tile)
+        if tile in self._plans:
+            return self._plans[tile]
+        L, st = lib(), _stream()
+        dev = self.device
+        with torch.cuda.device(dev):
+            if len(tile) == 2:
+                if self.grid_shape is None:
+                    raise RuntimeError("2-D tiles need a grid-shaped graph")
+                h, w = self.grid_shape
+                th, tw = tile
+                nt = -(-h // th) * -(-w // tw)
+                order = torch.empty(self.n_dst, dtype=torch.int32, device=dev)
+                tile_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+                check(L.gwen_grid_tiles(h, w, th, tw, _ptr(order), _ptr(tile_ptr), st),
+                      "gwen_grid_tiles")
+            else:
+                rows = tile[0]
+                nt = -(-self.n_dst // rows)
+                order = None
+                tile_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+                check(L.gwen_uniform_tiles(self.n_dst, rows, _ptr(tile_ptr), st),
+                      "gwen_uniform_tiles")
+            m = self.num_messages
+            need = C.c_size_t()
+            check(L.gwen_tile_plan_workspace_bytes(self.n_dst, m, nt, C.byref(need)),
+                  "gwen_tile_plan_workspace_bytes")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            tsrc_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+            tsrc_full = torch.empty(m, dtype=torch.int32, device=dev)
+            msg = torch.empty(m, dtype=torch.int64, device=dev)
+            status = torch.zeros(2, dtype=torch.int32, device=dev)
+            check(L.gwen_tile_plan_build(_ptr(self.rowptr), _ptr(self.src), _ptr(self.w),
+                                         _ptr(order), _ptr(tile_ptr), nt, self.n_dst, m,
+                                         _ptr(tsrc_ptr), _ptr(tsrc_full), _ptr(msg), _ptr(status),
+                                         _ptr(ws), need.value, st), "gwen_tile_plan_build")
+            total, max_src = status.tolist()  # one-time sync
+            tsrc = tsrc_full[:total].clone()
+            del tsrc_full, ws
+        plan = TilePlan(order, tile_ptr, tsrc_ptr, tsrc, msg, self.n_dst, max_src, total)
+        self._plans[tile] = plan
+        return plan
+
+
+def _build(edge_index: torch.Tensor, num_nodes: int, flags: int,
+           dis_in: Optional[torch.Tensor] = None) -> GraphCSR:
+    _require_cuda(edge_index, "edge_index")
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
+    ei = edge_index.contiguous()
+    e = ei.size(1)
+    dev = ei.device
+    L = lib()
+    with torch.cuda.device(dev):
+        st = _stream()
+        need = C.c_size_t()
+        check(L.gwen_graph_workspace_bytes(num_nodes, e, flags, C.byref(need)),
+              "gwen_graph_workspace_bytes")
+        cap = e + (num_nodes if flags & _lib.GRAPH_ADD_SELF_LOOPS else 0)
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+        src = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        perm = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+        w = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+        dis = dis_in if dis_in is not None else torch.empty(num_nodes, dtype=torch.float32, device=dev)
+        status = torch.zeros(2, dtype=torch.int32, device=dev)
+        check(L.gwen_graph_build(_ptr(ei), e, num_nodes, flags, _ptr(rowptr), _ptr(src), _ptr(perm),
+                                 _ptr(dis), _ptr(w), _ptr(status), _ptr(ws), need.value, st),
+              "gwen_graph_build")
+        bad, m = status.tolist()  # one-time sync per graph
+    if bad:
+        raise IndexError("edge_index has %d entries outside [0, %d)" % (bad, num_nodes))
+    return GraphCSR(rowptr, src[:m], w[:m], dis, perm[:m], num_nodes, num_nodes, m, flags,
+                    edge_index=ei)
+
+
+def _detect_grid(edge_index: torch.Tensor, num_nodes: int) -> Optional[Tuple[int, int]]:
+    """(H, W) if edge_index is exactly grid(H, W) (with or without its self loops), else None."""
+    e = edge_index.size(1)
+    if num_nodes < 4 or e < 12:
+        return None
+    head = edge_index[:, :4].tolist()
+    if head[0][:3] != [0, 0, 0]:
+        return None
+    with_loops = head[1][0] == 0
+    w = head[1][2] if with_loops else head[1][1]
+    if w < 2 or num_nodes % w:
+        return None
+    h = num_nodes // w
+    if h < 2:
+        return None
+    full = grid_edge_count(h, w)
+    if e != (full if with_loops else full - num_nodes):
+        return None
+    ref = grid(h, w, edge_index.device)
+    if not with_loops:
+        ref = ref[:, ref[0] != ref[1]]
+    return (h, w) if torch.equal(ref, edge_index) else None
+
+
+def build_graph(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True,
+                improved: bool = False, grid_shape: Optional[Tuple[int, int]] = "auto") -> GraphCSR:
+    """Run the K0 preprocessor.  ``grid_shape`` ("auto" = detect) enables 2-D tile plans."""
+    flags = (_lib.GRAPH_ADD_SELF_LOOPS if add_self_loops else 0) | (_lib.GRAPH_IMPROVED if improved else 0)
+    g = _build(edge_index, num_nodes, flags)
+    if grid_shape == "auto":
+        grid_shape = _detect_grid(g.edge_index, num_nodes)
+    g.grid_shape = grid_shape
+    return g
+
+
+# ---------------------------------------------------------------------------------------------
+# cache: GCNConv(cached=False) semantics without recomputing the graph every layer call
+# ---------------------------------------------------------------------------------------------
+class _CacheEntry:
+    __slots__ = ("tensor", "version", "num_nodes", "flags", "graph")
+
+
+_CACHE: list = []
+_CACHE_SIZE = 8
+
+
+def clear_graph_cache() -> None:
+    _CACHE.clear()
+
+
+def get_graph(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True,
+              improved: bool = False) -> GraphCSR:
+    """CSR for ``edge_index``, memoised on the tensor's storage + version counter.
+
+    PyG recomputes the normalisation on every call (``cached=False``, the GWEN default).  The
+    result only depends on ``edge_index``; the cache keeps a strong reference to the tensor it
+    was built from, so a hit means "same live memory, same version" and stays correct when a
+    loader hands a different ``edge_index`` every iteration (reference models_gnn.py:359).
+    """
+    flags = (_lib.GRAPH_ADD_SELF_LOOPS if add_self_loops else 0) | (_lib.GRAPH_IMPROVED if improved else 0)
+    for i, ent in enumerate(_CACHE):
+        t = ent.tensor
+        if (t.data_ptr() == edge_index.data_ptr() and t.shape == edge_index.shape
+                and t.stride() == edge_index.stride() and t.device == edge_index.device
+                and ent.version == edge_index._version and ent.num_nodes == num_nodes
+                and ent.flags == flags):
+            if i:
+                _CACHE.insert(0, _CACHE.pop(i))
+            return ent.graph
+    g = build_graph(edge_index, num_nodes, add_self_loops, improved)
+    ent = _CacheEntry()
+    ent.tensor, ent.version, ent.num_nodes, ent.flags, ent.graph = edge_index, edge_index._version, num_nodes, flags, g
+    _CACHE.insert(0, ent)
+    del _CACHE[_CACHE_SIZE:]
+    return g

@@ -1,0 +1,146 @@
+"""``GCNConv``: drop-in for ``torch_geometric.nn.GCNConv`` as GWEN uses it.
+
+Reference boundary: imported at ``src/gwen/models_gnn.py:19``, constructed as
+``GCNConv(in_channels, out_channels)`` at ``:118-130`` / ``:172-184`` and called as
+``conv(x, edge_index)`` at ``:147-149`` / ``:204-206``.  Same constructor arguments, same
+parameter names (``lin.weight [out, in]``, ``bias [out]``) and glorot/zeros initialisation
+(SURVEY.md Appendix A.1), so ``state_dict``s are interchangeable with the PyG module.
+
+The arithmetic is ``D^-1/2 (A + I) D^-1/2 (x W^T) + b`` computed by libgwen_b200's kernels:
+graph preprocessing once per ``edge_index`` (K0), then per call one projection (K2) and one
+deterministic segment-reduce aggregation (K1) -- aggregating on whichever side of the
+projection is narrower -- with bias and an optional fused ReLU in the last kernel's epilogue.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from .graph import GraphCSR, get_graph
+
+__all__ = ["GCNConv", "gcn_conv"]
+
+
+class _GCNConvFn(torch.autograd.Function):
+    """y = epi(A_hat (x W^T) + b); backward per SURVEY.md Appendix A.7."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], graph: GraphCSR,
+                relu: bool, agg_first: bool):
+        if agg_first:      # (A_hat x) W^T: aggregate at the narrower input width
+            h = ops.aggregate(graph, x)
+            y = ops.linear(h, weight, bias, relu)
+            saved_in = h
+        else:              # A_hat (x W^T): aggregate at the narrower output width
+            h = ops.linear(x, weight)
+            y = ops.aggregate(graph, h, bias, relu)
+            saved_in = x
+        ctx.graph, ctx.relu, ctx.agg_first = graph, relu, agg_first
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(saved_in, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        saved_in, weight, y = ctx.saved_tensors
+        graph_t = ctx.graph.transposed()
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = ops.relu_bwd_(y, dy.clone())
+        db = ops.bias_grad(dy).to(weight.dtype) if ctx.has_bias else None
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        if ctx.agg_first:
+            dw = ops.linear_bwd_weight(dy, saved_in)              # dW = dy^T (A_hat x)
+            if need_dx:
+                dx = ops.aggregate(graph_t, ops.linear_bwd_data(dy, weight))
+        else:
+            dh = ops.aggregate(graph_t, dy)                       # A_hat^T dy
+            dw = ops.linear_bwd_weight(dh, saved_in)              # dW = dh^T x
+            if need_dx:
+                dx = ops.linear_bwd_data(dh, weight)
+        return dx, dw.to(weight.dtype), db, None, None, None
+
+
+def gcn_conv(x: Tensor, graph: GraphCSR, weight: Tensor, bias: Optional[Tensor] = None,
+             relu: bool = False, agg_first: Optional[bool] = None) -> Tensor:
+    """Functional form on a prebuilt graph handle."""
+    if agg_first is None:
+        agg_first = weight.shape[1] < weight.shape[0]
+    return _GCNConvFn.apply(x, weight, bias, graph, relu, agg_first)
+
+
+class _Linear(torch.nn.Module):
+    """Weight holder named like PyG's ``Linear(in, out, bias=False)`` (``lin.weight``)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = torch.nn.Parameter(torch.empty(out_channels, in_channels))
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.in_channels + self.out_channels))  # glorot uniform
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return ops.linear(x, self.weight)
+
+    def extra_repr(self):
+        return "%d, %d, bias=False" % (self.in_channels, self.out_channels)
+
+
+class GCNConv(torch.nn.Module):
+    """``GCNConv(in_channels, out_channels, improved=False, cached=False, add_self_loops=True,
+    normalize=True, bias=True)``; ``forward(x [..., N, F_in], edge_index int64 [2, E]) ->
+    [..., N, F_out]``.  ``relu=True`` (extension) fuses the ``torch.relu`` the reference model
+    applies after the layer into the kernel epilogue.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False,
+                 cached: bool = False, add_self_loops: bool = True, normalize: bool = True,
+                 bias: bool = True, **kwargs):
+        super().__init__()
+        if kwargs:
+            raise TypeError("unsupported GCNConv arguments: %s" % sorted(kwargs))
+        if not normalize:
+            raise NotImplementedError("GCNConv(normalize=False) is not part of the GWEN path")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached, self.add_self_loops, self.normalize = improved, cached, add_self_loops, normalize
+        self.lin = _Linear(in_channels, out_channels)
+        if bias:
+            self.bias = torch.nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self._cached_graph: Optional[GraphCSR] = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        if self.bias is not None:
+            with torch.no_grad():
+                self.bias.zero_()
+        self._cached_graph = None
+
+    def forward(self, x: Tensor, edge_index, edge_weight: Optional[Tensor] = None,
+                relu: bool = False) -> Tensor:
+        if edge_weight is not None:
+            raise NotImplementedError("edge_weight is not used on the GWEN path")
+        if not x.is_cuda:
+            raise RuntimeError("gwen_b200.GCNConv runs on CUDA tensors only (no CPU fallback)")
+        if isinstance(edge_index, GraphCSR):
+            graph = edge_index
+        elif self.cached and self._cached_graph is not None:
+            graph = self._cached_graph
+        else:
+            graph = get_graph(edge_index, x.size(-2), self.add_self_loops, self.improved)
+            if self.cached:
+                self._cached_graph = graph
+        return gcn_conv(x, graph, self.lin.weight, self.bias, relu)
+
+    def __repr__(self):
+        return "%s(%d, %d)" % (self.__class__.__name__, self.in_channels, self.out_channels)

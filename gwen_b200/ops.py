@@ -1,0 +1,179 @@
+"""Functional wrappers over the C ABI: aggregate (K1), linear (K2), backward pieces, row moves.
+
+Every function takes CUDA tensors, launches on the current stream of the tensors' device and
+returns a torch-allocated result.  Nothing here computes with torch ops: a missing library or a
+CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
+
+__all__ = ["aggregate", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad",
+           "rows_gather", "rows_scatter_", "dtype_code"]
+
+_DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
+
+# Which K1 kernel `aggregate` uses: "auto" (tiled when the graph is a grid and rows are
+# 16-byte multiples), "rows", "tiled".  bench.py / tests override it explicitly.
+DEFAULT_AGG_KERNEL = "auto"
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise TypeError("gwen_b200 supports float32 and bfloat16, got %s" % dt) from None
+
+
+def _as_3d(x: torch.Tensor):
+    """[..., N, F] -> contiguous [B, N, F] view + the leading shape."""
+    if x.dim() < 2:
+        raise ValueError("expected [..., N, F]")
+    lead = x.shape[:-2]
+    x3 = x.reshape((-1,) + tuple(x.shape[-2:])).contiguous()
+    return x3, lead
+
+
+def _bias32(bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if bias is None:
+        return None
+    return bias.detach().to(torch.float32).contiguous()
+
+
+def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              relu: bool = False, kernel: Optional[str] = None, tile=None, slab: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[..., i, :] = epi(sum_s w[s] * x[..., src[s], :] + bias) over the CSR of ``graph``."""
+    _require_cuda(x, "x")
+    x3, lead = _as_3d(x)
+    b, n_src, f = x3.shape
+    if n_src != graph.n_src:
+        raise ValueError("x has %d rows, graph expects %d source rows" % (n_src, graph.n_src))
+    code = dtype_code(x3.dtype)
+    kernel = kernel or DEFAULT_AGG_KERNEL
+    esz = x3.element_size()
+    if kernel == "auto":
+        kernel = "tiled" if (graph.grid_shape is not None and (f * esz) % 16 == 0 and f * esz >= 128) else "rows"
+    bias32 = _bias32(bias)
+    with torch.cuda.device(x3.device):
+        if out is None:
+            out = torch.empty((b, graph.n_dst, f), dtype=x3.dtype, device=x3.device)
+        epi = _lib.EPI_RELU if relu else _lib.EPI_NONE
+        if kernel == "tiled":
+            plan = graph.tile_plan(tile)
+            check(lib().gwen_aggregate_tiled_fwd(C.byref(plan.struct), _ptr(graph.rowptr), _ptr(x3),
+                                                 _ptr(out), b, n_src, f, f, n_src * f, f,
+                                                 graph.n_dst * f, code, _ptr(bias32), epi, slab,
+                                                 _stream()), "gwen_aggregate_tiled_fwd")
+        elif kernel == "rows":
+            check(lib().gwen_aggregate_fwd(_ptr(graph.rowptr), _ptr(graph.src), _ptr(graph.w),
+                                           _ptr(graph.order), _ptr(x3), _ptr(out), b, graph.n_dst,
+                                           n_src, f, f, n_src * f, f, graph.n_dst * f, code,
+                                           _ptr(bias32), epi, _stream()), "gwen_aggregate_fwd")
+        else:
+            raise ValueError("unknown aggregate kernel %r" % kernel)
+    return out.reshape(tuple(lead) + (graph.n_dst, f))
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           relu: bool = False) -> torch.Tensor:
+    """y = epi(x @ weight.T + bias); x [..., K], weight [N_out, K]."""
+    _require_cuda(x, "x")
+    _require_cuda(weight, "weight")
+    k = x.shape[-1]
+    n_out = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError("weight is %s, x has %d features" % (tuple(weight.shape), k))
+    x2 = x.reshape(-1, k).contiguous()
+    wt = weight.detach().to(x2.dtype).contiguous()
+    code = dtype_code(x2.dtype)
+    bias32 = _bias32(bias)
+    with torch.cuda.device(x2.device):
+        y = torch.empty((x2.shape[0], n_out), dtype=x2.dtype, device=x2.device)
+        check(lib().gwen_linear_fwd(_ptr(x2), _ptr(wt), _ptr(y), x2.shape[0], k, n_out, k, k, n_out,
+                                    code, _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
+              "gwen_linear_fwd")
+    return y.reshape(tuple(x.shape[:-1]) + (n_out,))
+
+
+def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dx = dy @ weight; dy [..., N_out], weight [N_out, K]."""
+    n_out, k = weight.shape
+    dy2 = dy.reshape(-1, n_out).contiguous()
+    wt = weight.detach().to(dy2.dtype).contiguous()
+    with torch.cuda.device(dy2.device):
+        dx = torch.empty((dy2.shape[0], k), dtype=dy2.dtype, device=dy2.device)
+        check(lib().gwen_linear_bwd_data(_ptr(dy2), _ptr(wt), _ptr(dx), dy2.shape[0], k, n_out, n_out,
+                                         k, k, dtype_code(dy2.dtype), _stream()),
+              "gwen_linear_bwd_data")
+    return dx.reshape(tuple(dy.shape[:-1]) + (k,))
+
+
+def linear_bwd_weight(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dw[n, k] = sum_m dy[m, n] x[m, k] in fp32 (fixed split order -> deterministic)."""
+    n_out, k = dy.shape[-1], x.shape[-1]
+    dy2 = dy.reshape(-1, n_out).contiguous()
+    x2 = x.reshape(-1, k).contiguous()
+    m = dy2.shape[0]
+    with torch.cuda.device(dy2.device):
+        need = C.c_size_t()
+        check(lib().gwen_linear_bwd_weight_workspace_bytes(m, k, n_out, C.byref(need)), "wgrad ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device)
+        dw = torch.empty((n_out, k), dtype=torch.float32, device=dy2.device)
+        check(lib().gwen_linear_bwd_weight(_ptr(dy2), _ptr(x2), _ptr(dw), m, k, n_out, n_out, k, k,
+                                           dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
+              "gwen_linear_bwd_weight")
+    return dw
+
+
+def relu_bwd_(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """In place: dy[y <= 0] = 0."""
+    f = y.shape[-1]
+    y2, dy2 = y.reshape(-1, f), dy.reshape(-1, f)
+    assert y2.is_contiguous() and dy2.is_contiguous()
+    with torch.cuda.device(y.device):
+        check(lib().gwen_relu_bwd(_ptr(y2), _ptr(dy2), y2.shape[0], f, f, f, dtype_code(y.dtype),
+                                  _stream()), "gwen_relu_bwd")
+    return dy
+
+
+def bias_grad(dy: torch.Tensor) -> torch.Tensor:
+    f = dy.shape[-1]
+    dy2 = dy.reshape(-1, f).contiguous()
+    with torch.cuda.device(dy2.device):
+        need = C.c_size_t()
+        check(lib().gwen_bias_grad_workspace_bytes(dy2.shape[0], f, C.byref(need)), "bias ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device)
+        db = torch.empty(f, dtype=torch.float32, device=dy2.device)
+        check(lib().gwen_bias_grad(_ptr(dy2), _ptr(db), dy2.shape[0], f, f, dtype_code(dy2.dtype),
+                                   _ptr(ws), need.value, _stream()), "gwen_bias_grad")
+    return db
+
+
+def rows_gather(x: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """buf[b, j, :] = x[b, idx[j], :] for x [B, N, F] (halo pack)."""
+    b, n, f = x.shape
+    assert x.is_contiguous() and idx.dtype == torch.int32
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.empty((b, idx.numel(), f), dtype=x.dtype, device=x.device)
+        check(lib().gwen_rows_gather(_ptr(x), _ptr(idx), _ptr(out), b, idx.numel(), f, f, n * f,
+                                     dtype_code(x.dtype), _stream()), "gwen_rows_gather")
+    return out
+
+
+def rows_scatter_(x: torch.Tensor, idx: torch.Tensor, buf: torch.Tensor) -> torch.Tensor:
+    """x[b, idx[j], :] = buf[b, j, :] (halo unpack)."""
+    b, n, f = x.shape
+    assert x.is_contiguous() and buf.is_contiguous() and idx.dtype == torch.int32
+    with torch.cuda.device(x.device):
+        check(lib().gwen_rows_scatter(_ptr(buf), _ptr(idx), _ptr(x), b, idx.numel(), f, f, n * f,
+                                      dtype_code(x.dtype), _stream()), "gwen_rows_scatter")
+    return x

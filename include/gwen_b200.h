@@ -1,0 +1,204 @@
+/*
+ * gwen_b200.h -- C ABI of libgwen_b200.so: the B200 (sm_100a) implementation of the GWEN
+ * GCN message-passing hot path.
+ *
+ * The reference (MeteoSwiss/GWEN) has no FFI for this path: the boundary is the Python class
+ * torch_geometric.nn.GCNConv imported at reference src/gwen/models_gnn.py:19, constructed at
+ * :118-130 / :172-184 and called as conv(x, edge_index) at :147-149 / :204-206.  Each entry
+ * point below names the step of that call it replaces (the
+ * PyG-2.3.1 implementation itself is an un-vendored dependency, requirements/environment.yml:552).
+ * gwen_b200/nn.py is the ctypes host side that mirrors GCNConv on top of these functions;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host.  The caller (PyTorch's caching allocator) owns every
+ *     buffer; the library never allocates device memory that outlives a call.
+ *   - every launch function takes the CUDA stream (a cudaStream_t passed as void*); calls are
+ *     stream-ordered, never synchronise, and are CUDA-graph capturable.
+ *   - return value: GWEN_OK (0) or a negative GWEN_E_* code; the message is available from
+ *     gwen_last_error() (thread local).  Nothing throws across the ABI.  There is no CPU
+ *     fallback: without a device every launch function returns GWEN_E_CUDA.
+ *   - matrices are row-major; "ld" is the row pitch in ELEMENTS; batch strides are in elements.
+ */
+#ifndef GWEN_B200_H_
+#define GWEN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWEN_ABI_VERSION 1
+
+enum {
+  GWEN_OK = 0,
+  GWEN_E_BADARG = -1,    /* null pointer, negative size, index range ... */
+  GWEN_E_ALIGN = -2,     /* pointer / pitch not aligned as documented     */
+  GWEN_E_DTYPE = -3,     /* unknown dtype code                             */
+  GWEN_E_CUDA = -4,      /* CUDA runtime / launch error                    */
+  GWEN_E_NOSUPPORT = -5, /* valid request this build cannot serve          */
+  GWEN_E_WORKSPACE = -6  /* workspace too small                            */
+};
+
+enum { GWEN_F32 = 0, GWEN_BF16 = 1 };
+
+/* flags of gwen_graph_build */
+enum {
+  GWEN_GRAPH_ADD_SELF_LOOPS = 1u, /* GCNConv(add_self_loops=True), the default GWEN uses      */
+  GWEN_GRAPH_IMPROVED = 2u,       /* GCNConv(improved=True): self-loop weight 2               */
+  GWEN_GRAPH_TRANSPOSE = 4u       /* build the CSR of the transposed graph (backward pass)    */
+};
+
+/* flags of the epilogue argument of aggregate / linear */
+enum { GWEN_EPI_NONE = 0, GWEN_EPI_RELU = 1 };
+
+int gwen_version(void);
+/* Last error message of the calling thread ("" if none).  Pointer stays valid until the next
+ * failing call on this thread. */
+const char* gwen_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K0  graph preprocessor.  Replaces, once per edge_index instead of once per layer call,
+ * add_remaining_self_loops + ones + scatter(deg) + pow(-0.5) + dis[row]*ew*dis[col]
+ *  and produces the destination-sorted CSR the
+ * aggregation kernels walk (Appendix B.3).
+ *
+ * edge_index: int64 [2, E] row-major, row 0 = source, row 1 = destination (PyG flow
+ *             source_to_target).  With GWEN_GRAPH_TRANSPOSE the roles are swapped.
+ * Outputs (capacity Ecap = E + N when ADD_SELF_LOOPS else E):
+ *   rowptr int32[N+1]   segment offsets per destination; rowptr[N] = E' (messages)
+ *   src    int32[Ecap]  source node of each message, destination-major, STABLE in edge_index'
+ *                       order (surviving input edges in list order, the self loop last)
+ *   perm   int64[Ecap]  (nullable) position of the message in edge_index' (after A.2)
+ *   dis    fp32[N]      deg^-1/2, fp64-computed and rounded once (0 for deg 0)
+ *   w      fp32[Ecap]   (nullable) dis[src] * fill * dis[dst] per message, CSR order
+ *   status int32[2]     [0] = number of out-of-range indices seen (must be 0), [1] = E'
+ * ws: scratch of at least gwen_graph_workspace_bytes(...) bytes, 256-byte aligned.
+ * Requires N < 2^31 - 1 and E + N < 2^31.
+ */
+int gwen_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges, uint32_t flags,
+                               size_t* bytes_out_host);
+int gwen_graph_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                     uint32_t flags, int32_t* rowptr, int32_t* src, int64_t* perm, float* dis,
+                     float* w, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* Graph builders whose edge ORDER is part of the parity contract.
+ * gwen_complete_edges: erdos_renyi_graph(N, edge_prob=1) as called at reference
+ *   src/gwen/utils.py:176 -> all (i, j), i != j, sorted by (row, col); out int64 [2, N(N-1)].
+ * gwen_grid_edges: PyG grid(H, W) 8-neighbour mesh incl. self loops, node id = r*W + c, sorted
+ *   by (row, col); out int64 [2, gwen_grid_edge_count(H, W)]. */
+int64_t gwen_grid_edge_count(int64_t height, int64_t width);
+int gwen_grid_edges(int64_t height, int64_t width, int64_t* edge_index_out, void* stream);
+int gwen_complete_edges(int64_t num_nodes, int64_t* edge_index_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  deterministic segment-reduce aggregation.  Replaces index_select + message multiply +
+ * scatter_add_ + bias + relu:
+ *   out[b, i, :] = epi( sum_{s in [rowptr[i], rowptr[i+1])} w[s] * x[b, src[s], :]  + bias )
+ * Summation runs in CSR order with fp32 accumulation; for fp32 the products and adds are
+ * formed unfused (mul.rn then add.rn) so the result equals the CPU scatter_add_ order bitwise.
+ * x: [B, n_src, F] (pitch ldx, batch stride x_bstride), out: [B, n_dst, F] (ldo, o_bstride).
+ * bias: fp32[F] or NULL.  dtype: GWEN_F32 / GWEN_BF16 (x and out share it).
+ * order: int32[n_dst] or NULL -- the order in which destination rows are assigned to warps
+ *        (a locality hint, e.g. the 2-D tile order of gwen_grid_tiles); results do not depend on it.
+ */
+int gwen_aggregate_fwd(const int32_t* rowptr, const int32_t* src, const float* w,
+                       const int32_t* order, const void* x, void* out, int64_t batch,
+                       int64_t n_dst, int64_t n_src, int64_t feat, int64_t ldx, int64_t x_bstride,
+                       int64_t ldo, int64_t o_bstride, int dtype, const float* bias, int epilogue,
+                       void* stream);
+
+/* Tiled variant: destination rows are processed in tiles whose DISTINCT source rows are staged
+ * once in shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier), so a source
+ * row slab crosses L2->SM once per tile instead of once per message.  The plan is built once
+ * per graph from the CSR by gwen_tile_plan_build:
+ *   order    int32[n_dst]        (nullable = identity) destination processing order
+ *   tile_ptr int32[num_tiles+1]  tile t covers positions tile_ptr[t] .. tile_ptr[t+1] of order
+ *   tsrc_ptr int32[num_tiles+1]  offsets into tsrc
+ *   tsrc     int32[...]          distinct source rows of each tile, ascending
+ *   msg      uint64[E']          per CSR slot: low 32 bits = index of the source inside its
+ *                                tile's tsrc list, high 32 bits = the fp32 weight w[slot]
+ * All arrays are caller-allocated device memory (tsrc capacity = E' is always enough).
+ * The result is bitwise identical to gwen_aggregate_fwd. */
+typedef struct gwen_tile_plan {
+  int32_t num_tiles;
+  int32_t max_tile_src;    /* largest tsrc_ptr[t+1] - tsrc_ptr[t]; sizes the smem stage */
+  int64_t n_dst;
+  const int32_t* order;    /* device, nullable */
+  const int32_t* tile_ptr; /* device */
+  const int32_t* tsrc_ptr; /* device */
+  const int32_t* tsrc;     /* device */
+  const uint64_t* msg;     /* device */
+} gwen_tile_plan;
+
+int gwen_tile_plan_workspace_bytes(int64_t n_dst, int64_t num_messages, int64_t num_tiles,
+                                   size_t* bytes_out_host);
+/* status int32[2]: [0] = total distinct (tile, source) pairs = tsrc_ptr[num_tiles],
+ *                  [1] = max distinct sources of any tile. */
+int gwen_tile_plan_build(const int32_t* rowptr, const int32_t* src, const float* w,
+                         const int32_t* order, const int32_t* tile_ptr, int64_t num_tiles,
+                         int64_t n_dst, int64_t num_messages, int32_t* tsrc_ptr, int32_t* tsrc,
+                         uint64_t* msg, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+/* Tile layouts.  uniform: identity order, tile_rows destinations per tile (tile_ptr only).
+ * grid: 2-D th x tw blocks of an H x W grid graph (node id r*W + c), tiles row-major; writes
+ * order[H*W] and tile_ptr[ceil(H/th)*ceil(W/tw) + 1]. */
+int gwen_uniform_tiles(int64_t n_dst, int32_t tile_rows, int32_t* tile_ptr_out, void* stream);
+int gwen_grid_tiles(int64_t height, int64_t width, int32_t th, int32_t tw, int32_t* order_out,
+                    int32_t* tile_ptr_out, void* stream);
+/* slab_elems: feature columns staged per work item (0 = library default); must keep
+ * max_tile_src * slab_elems * sizeof(dtype) within the 227 KB shared-memory limit. */
+int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const int32_t* rowptr,
+                             const void* x, void* out, int64_t batch, int64_t n_src,
+                             int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo,
+                             int64_t o_bstride, int dtype, const float* bias, int epilogue,
+                             int32_t slab_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
+ * SURVEY.md table 2.3 row 6) and, through the epilogue, the bias add and ReLU when the
+ * projection runs after the aggregation:
+ *   y[m, n] = epi( sum_k x[m, k] * weight[n, k] + bias[n] )        x:[M,K]  weight:[Nout,K]
+ * GWEN_F32: fp32 in / fp32 accumulate / fp32 out.
+ * GWEN_BF16: bf16 in, fp32 accumulate (tcgen05 tensor cores, TMEM accumulators), bf16 out.
+ * gwen_linear_bwd_* are the two GEMMs of the backward pass (Appendix A.7):
+ *   dgrad: dx[m, k] = sum_n dy[m, n] * weight[n, k]
+ *   wgrad: dw[n, k] = sum_m dy[m, n] * x[m, k]      (fp32 output, deterministic split order)
+ */
+int gwen_linear_fwd(const void* x, const void* weight, void* y, int64_t m, int64_t k,
+                    int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int dtype,
+                    const float* bias, int epilogue, void* stream);
+int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
+                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
+                         void* stream);
+int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t m, int64_t k,
+                           int64_t n_out, int64_t lddy, int64_t ldx, int64_t lddw, int dtype,
+                           void* ws, size_t ws_bytes, void* stream);
+int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int64_t n_out,
+                                           size_t* bytes_out_host);
+
+/* Elementwise helpers of the backward pass: relu mask (dy *= y > 0) and bias gradient
+ * (db[f] = sum_rows dy[:, f], fixed-order tree, fp32 out). */
+int gwen_relu_bwd(const void* y, void* dy, int64_t rows, int64_t feat, int64_t ldy, int64_t lddy,
+                  int dtype, void* stream);
+int gwen_bias_grad(const void* dy, float* db, int64_t rows, int64_t feat, int64_t lddy, int dtype,
+                   void* ws, size_t ws_bytes, void* stream);
+int gwen_bias_grad_workspace_bytes(int64_t rows, int64_t feat, size_t* bytes_out_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * Halo exchange helpers for the row-band mesh partition (no reference counterpart; SURVEY.md
+ * section 8(e)): gather / scatter whole feature rows by index so the send and receive buffers
+ * are contiguous for ncclSend / ncclRecv.
+ *   pack:   buf[b, j, :] = x[b, idx[j], :]        unpack: x[b, idx[j], :] = buf[b, j, :]
+ */
+int gwen_rows_gather(const void* x, const int32_t* idx, void* buf, int64_t batch, int64_t n_idx,
+                     int64_t feat, int64_t ldx, int64_t x_bstride, int dtype, void* stream);
+int gwen_rows_scatter(const void* buf, const int32_t* idx, void* x, int64_t batch, int64_t n_idx,
+                      int64_t feat, int64_t ldx, int64_t x_bstride, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWEN_B200_H_ */
