@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GWEN GCN message-passing hot path on B200.
+
+Workload (BASELINE.json configs[1]): synthetic COSMO-2E-sized grid, 582 x 390 = 226 980 nodes,
+PyG ``grid`` 8-neighbour mesh (E' = 2 036 992 messages incl. self loops), F = 256, fp32.
+One step = one single-layer message+aggregate pass (``GCNConv.propagate``: gather source rows,
+scale by the symmetric GCN norm, segment-reduce into destinations, + bias) over the whole mesh.
+Metric: message-passing edges/s = E' x steps / time (whole job, all ranks).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA path, C ABI)
+  python bench.py --impl reference [--gpus N] ...                  # the reference's CPU path
+
+N > 1 (launched with torch.distributed.run, one rank per GPU): WEAK scaling -- every rank owns a
+582 x 390 row band of a (582 N) x 390 mesh and fetches its one-row halos from the neighbouring
+ranks over NCCL before each aggregation (gwen_b200/partition.py).
+
+Timing: W untimed steps, then exactly K steps bracketed by barrier + synchronize, CUDA events on
+the launching stream, max over ranks.  Inputs + outputs (465 MB) exceed the 126 MB L2, so no
+explicit flush is needed.  ``e2e`` repeats the measurement through the public layer API with
+pinned HOST buffers (H2D of x and D2H of the result inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FEAT = 582, 390, 256
+METRIC, UNIT = "gcn_message_passing_edges_per_s", "edges/s"
+WORKLOAD = ("cfg2: synthetic COSMO-2E grid 582x390 (226980 nodes, E'=2036992 messages incl. self "
+            "loops), F=256 fp32, single-layer message+aggregate (GCNConv.propagate)")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_agg_tiled_cfg2.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the benchmark runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.12)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 8]
+        window = "timed+e2e"
+        if len(rows) < 3:
+            rows = [r for _, r in self.rows if len(r) >= 8]
+            window = "whole run (timed region shorter than the sampling period)"
+        busy = [r for r in rows if r[3].isdigit() and int(r[3]) > 0] or rows
+        try:
+            sm = statistics.median(float(r[0]) for r in busy)
+            mx = max(float(r[1]) for r in busy)
+            pw = max(float(r[2]) for r in busy)
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "unparsable nvidia-smi output"}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in busy)]
+        return {"sm_mhz": sm, "sm_max_mhz": mx, "power_w_max": pw, "reasons": reasons,
+                "samples": len(busy), "window": window}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle restatement of the PyG op sequence on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_propagate_rate(rows: int, steps: int, warmup: int = 1):
+    """edges/s of index_select + scale + scatter_add_ + bias on a rows x W band of the mesh."""
+    import torch
+    from oracle import gcn_oracle as orc  # the checker, used here as the timed CPU reference
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = rows * W
+    ei = orc.grid(rows, W)
+    ei2, ew, _ = orc.gcn_norm(ei, n)
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(n, FEAT, generator=g)
+    bias = torch.randn(FEAT, generator=g) * 0.1
+    for _ in range(warmup):
+        orc.propagate(x, ei2, ew, n) + bias
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.propagate(x, ei2, ew, n) + bias
+    dt = time.perf_counter() - t0
+    return ei2.size(1) * steps / dt, dt / steps, ei2.size(1), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bound the run: one full-mesh step costs ~1 s on 8 cores; shrink to a row band if K is large
+    budget_s = 120.0
+    rate, per_step, _, cores = cpu_propagate_rate(64, 1, warmup=1)
+    est_full = (H * W * 9) / rate
+    rows = H if est_full * (args.steps + args.warmup) <= budget_s else \
+        max(16, min(H, int(H * budget_s / (est_full * (args.steps + args.warmup)))))
+    rate, per_step, edges, cores = cpu_propagate_rate(rows, args.steps, warmup=max(1, min(args.warmup, 3)))
+    sample = "full 582x390 mesh per step" if rows == H else \
+        "%dx390 row band of the mesh per step (%d messages), rate is per-edge so no scaling needed" % (rows, edges)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "arm": "oracle port of the PyG-2.3.1 "
+                                        "GCNConv.propagate op sequence on host CPU (torch_geometric is not installable here)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gwen_b200 as gw
+    from gwen_b200 import ops, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    gen = torch.Generator().manual_seed(23 + rank)
+    bias = (torch.randn(FEAT, generator=torch.Generator().manual_seed(23)) * 0.1).to(dev)
+    # ---- graph: global mesh of (H * world) x W, this rank's band ---------------------------
+    gh = H * world
+    ei = gw.grid(gh, W, dev)
+    g_global = gw.build_graph(ei, gh * W)
+    launches_per_step = 1
+    if world == 1:
+        graph, hx, n_local = g_global, None, H * W
+    else:
+        ranges = partition.band_ranges(gh, W, world)
+        lg = partition.partition_graph(g_global, ranges[rank], (H, W))
+        hx = partition.HaloExchange(lg, ranges)
+        graph, n_local = lg.graph, lg.n_local
+        launches_per_step = 1 + len(hx.send_idx)
+        del g_global, ei
+    n_own, msgs_local = graph.n_dst, graph.num_messages
+    x = torch.empty(n_local, FEAT, device=dev)
+    x[:n_own] = torch.randn(n_own, FEAT, generator=gen).to(dev)
+    out = torch.empty(n_own, FEAT, device=dev)
+    plan = graph.tile_plan()  # built once, outside the timed region (one-time preprocessing)
+
+    def step():
+        if hx is not None:
+            hx.exchange(x)
+        ops.aggregate(graph, x, bias, kernel="tiled", out=out)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    tot = torch.tensor([float(msgs_local)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = ms.item()
+    total_msgs = tot.item()
+    value = total_msgs * args.steps / (ms_total * 1e-3)
+
+    # ---- per-launch time of the dominant kernel (events around each launch, same stream) -----
+    per = []
+    for _ in range(min(50, max(10, args.steps))):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.aggregate(graph, x, bias, kernel="tiled", out=out)
+        b.record()
+        per.append((a, b))
+    torch.cuda.synchronize()
+    k_us = statistics.mean(a.elapsed_time(b) for a, b in per) * 1e3
+    alg_bytes = 2 * n_own * FEAT * 4 + 4 * (n_own + 1) + 8 * msgs_local + 4 * FEAT
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (k_us * 1e-6) / 1e9
+
+    # ---- e2e: public API with pinned host buffers, H2D + D2H inside the timed region ----------
+    x_host = torch.empty(n_local, FEAT).pin_memory()
+    x_host[:n_own] = x[:n_own].cpu()
+    out_host = torch.empty(n_own, FEAT).pin_memory()
+    conv = gw.GCNConv(FEAT, FEAT).to(dev)
+    with torch.no_grad():
+        conv.bias.copy_(bias)
+
+    def e2e_step():
+        x.copy_(x_host, non_blocking=True)
+        if hx is not None:
+            hx.exchange(x)
+        y = conv.propagate(graph, x)
+        out_host.copy_(y, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e_value = total_msgs * args.e2e_steps / (ms_e.item() * 1e-3)
+    t_wall1 = time.time()
+
+    if rank == 0:
+        clocks = sampler.stop(t_wall0, t_wall1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + "; weak scaling: one 582x390 "
+                       "row band per rank of a %dx390 mesh, one-row halo exchange (NCCL send/recv) per step" % gh,
+                       "l2": "inputs+outputs 465 MB per rank > 126 MB L2, no explicit flush",
+                       "tile_plan": {"tile": [8, 16], "run_len": plan.run_len,
+                                     "staged_rows_per_dst": round(plan.amplification, 3)}},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host[:n_own].numel() * 4 * world,
+                    "d2h_bytes_per_step": out_host.numel() * 4 * world, "steps": args.e2e_steps,
+                    "api": "gwen_b200.GCNConv.propagate(graph, x) with pinned host x / out"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"kernel": "k_agg_tiled<float,32>", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
+                         "us_per_launch": k_us, "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic": ncu_traffic()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, per_step, edges, cores = cpu_propagate_rate(H, 3, warmup=1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "3 full-mesh steps (582x390, F=256) of the oracle port, "
+                                              "%.2f s/step" % per_step}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

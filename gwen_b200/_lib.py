@@ -16,6 +16,7 @@ _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "linear.cu", "linear_tc.cu"]
+HEADERS = ["common.cuh", "tma.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
 GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4
@@ -55,9 +56,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 class TilePlanStruct(C.Structure):
-    _fields_ = [("num_tiles", C.c_int32), ("max_tile_src", C.c_int32), ("n_dst", C.c_int64),
-                ("order", C.c_void_p), ("tile_ptr", C.c_void_p), ("tsrc_ptr", C.c_void_p),
-                ("tsrc", C.c_void_p), ("msg", C.c_void_p)]
+    _fields_ = [("num_tiles", C.c_int32), ("run_len", C.c_int32), ("max_tile_runs", C.c_int32),
+                ("max_tile_rows", C.c_int32), ("max_tile_msgs", C.c_int32), ("reserved", C.c_int32),
+                ("n_dst", C.c_int64), ("tile_ptr", C.c_void_p), ("run_ptr", C.c_void_p),
+                ("run_start", C.c_void_p), ("trec", C.c_void_p), ("tmsg", C.c_void_p),
+                ("tmsg_base", C.c_void_p)]
 
 
 _p, _i64, _i32, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_int, C.c_size_t
@@ -74,11 +77,11 @@ PROTOTYPES = {
     "gwen_aggregate_fwd": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64,
                                   _i64, _i64, _int, _p, _int, _p]),
     "gwen_tile_plan_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
-    "gwen_tile_plan_build": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p,
-                                    _sz, _p]),
+    "gwen_tile_plan_build": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p,
+                                    _p, _p, _p, _sz, _p]),
     "gwen_uniform_tiles": (_int, [_i64, _i32, _p, _p]),
     "gwen_grid_tiles": (_int, [_i64, _i64, _i32, _i32, _p, _p, _p]),
-    "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _p, _i64, _i64, _i64,
+    "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _i64, _i64, _i64,
                                         _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),

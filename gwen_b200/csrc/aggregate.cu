@@ -12,10 +12,13 @@
 //                deg x to (distinct sources / tile rows) x; 2+ CTAs per SM overlap one CTA's
 //                staging with another's reduction.
 // Both accumulate in fp32 in CSR order with unfused mul.rn/add.rn (bitwise == CPU scatter_add_).
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gwen {
 namespace {
@@ -250,26 +253,36 @@ int dispatch_rows(const AggArgs& a, cudaStream_t st) {
 }
 
 // ---- k_agg_tiled ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+struct TiledArgs {
+  const int32_t* tile_ptr;
+  const int32_t* run_ptr;
+  const int32_t* run_start;
+  const int4* trec;       // per position p: {dst row, message offset inside the tile, degree, 0}
+  const uint64_t* tmsg;   // messages in processing order: low 32 = staged row, high 32 = weight
+  const int32_t* tmsg_base;
+  void* out;
+  const float* bias;
+  int64_t batch, feat, ldo, o_bstride;
+  int num_tiles, slabs, slab_elems, run_len, relu;
+  uint32_t stage_bytes;  // one data stage = max_tile_runs * run_len * slab bytes
+  uint32_t rec_bytes;    // one metadata buffer: records, then messages
+  uint32_t meta_bytes;
+  int num_stages;
+};
+
+__device__ __forceinline__ int4 lds_i4(uint32_t saddr) {
+  int4 r;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(saddr));
+  return r;
 }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+__device__ __forceinline__ uint2 lds_u2(uint32_t saddr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
+  return r;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra W_%=;\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-// One bulk asynchronous copy global -> shared, completing `bytes` on the mbarrier.
+// Plain bulk copy global -> shared (contiguous bytes, multiple of 16), completing on `bar`.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
                                          uint32_t bar) {
   asm volatile(
@@ -279,105 +292,165 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
-struct TiledArgs {
-  const int32_t* rowptr;
-  const int32_t* order;
-  const int32_t* tile_ptr;
-  const int32_t* tsrc_ptr;
-  const int32_t* tsrc;
-  const uint64_t* msg;
-  const void* x;
-  void* out;
-  const float* bias;
-  int64_t batch, feat, ldx, x_bstride, ldo, o_bstride;
-  int num_tiles, slabs, slab_elems, relu;
-};
-
-// Work item = (batch b, feature slab, tile).  A slab is CH*32 16-byte chunks wide at most.
-template <typename T, int CH>
-__global__ void __launch_bounds__(256) k_agg_tiled(TiledArgs a) {
+// Persistent, warp-specialised CTA; work item = (tile, batch b, feature slab), tile-major.
+// Shared memory holds NS data stages and two metadata buffers (row records + messages of a tile).
+//   producer (last warp, one lane): for every item waits for its stage to be empty, then issues
+//     one TMA tensor copy per run of consecutive source rows (completing on full[stage]); when
+//     the item starts a new tile it first brings the tile's records and message list with two
+//     plain bulk copies (meta_full).
+//   consumers (all other warps): wait full[stage]; each sub-warp of LPR lanes reduces destination
+//     rows out of shared memory -- record -> messages (broadcast LDS.64) -> source slabs
+//     (LDS.128) -> fp32 accumulate in CSR order -> STG.128 -- then one lane per warp arrives on
+//     empty[stage].  No block-wide barrier: a fast warp runs up to NS-1 items ahead.
+template <typename T, int LPR>
+__global__ void __launch_bounds__(1024, 1) k_agg_tiled(const __grid_constant__ CUtensorMap xmap,
+                                                       TiledArgs a) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_storage;
-  const uint32_t bar = smem_u32(&bar_storage);
-  const uint32_t stage = smem_u32(smem);
+  constexpr int RPW = 32 / LPR;
+  constexpr int U = 5;      // messages in flight per row
+  constexpr int MAXS = 8;   // most data stages
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAXS], empty_bar[MAXS], mfull_bar[2], mempty_bar[2];
+  const int ns = a.num_stages;
+  const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t meta0 = stage0 + uint32_t(ns) * a.stage_bytes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ncw = nwarps - 1;  // consumer warps
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_prefetch_desc(&xmap);
+    for (int i = 0; i < ns; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), ncw);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&mfull_bar[i]), 1);
+      mbar_init(smem_u32(&mempty_bar[i]), ncw);
+    }
+    mbar_fence_init();
   }
   __syncthreads();
-  uint32_t parity = 0;
-  const int64_t items = a.batch * a.slabs * int64_t(a.num_tiles);
-  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
-    const int t = static_cast<int>(it % a.num_tiles);
-    const int slab = static_cast<int>((it / a.num_tiles) % a.slabs);
-    const int64_t b = it / (int64_t(a.num_tiles) * a.slabs);
-    const int64_t f0 = int64_t(slab) * a.slab_elems;
-    const int cols = static_cast<int>(imin64(a.slab_elems, a.feat - f0));
-    const uint32_t row_bytes = cols * sizeof(T);
-    const int s_beg = __ldg(a.tsrc_ptr + t), s_end = __ldg(a.tsrc_ptr + t + 1);
-    const T* xb = static_cast<const T*>(a.x) + b * a.x_bstride + f0;
-    // stage: one bulk copy per distinct source row slab
-    if (threadIdx.x == 0) mbar_expect_tx(bar, uint32_t(s_end - s_beg) * row_bytes);
-    for (int i = s_beg + threadIdx.x; i < s_end; i += blockDim.x)
-      bulk_g2s(stage + uint32_t(i - s_beg) * row_bytes, xb + int64_t(__ldg(a.tsrc + i)) * a.ldx,
-               row_bytes, bar);
-    mbar_wait(bar, parity);
-    parity ^= 1;
-    // reduce: warp per destination row of the tile
-    const int p_beg = __ldg(a.tile_ptr + t), p_end = __ldg(a.tile_ptr + t + 1);
-    const int nchunk = cols / VN;  // 16-byte chunks in this slab
-    for (int p = p_beg + warp; p < p_end; p += nwarps) {
-      const int64_t d = a.order ? __ldg(a.order + p) : p;
-      const int beg = __ldg(a.rowptr + d), end = __ldg(a.rowptr + d + 1);
-      float acc[CH][VN];
-      bool on[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        on[c] = c * 32 + lane < nchunk;
-#pragma unroll
-        for (int k = 0; k < VN; ++k) acc[c][k] = 0.0f;
+  const uint32_t slab_bytes = a.slab_elems * sizeof(T);
+  const uint32_t run_bytes = a.run_len * slab_bytes;
+  const int per_tile = static_cast<int>(a.batch) * a.slabs;
+  const int my_tiles = a.num_tiles > int(blockIdx.x)
+                           ? (a.num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+  const int64_t n_items = int64_t(my_tiles) * per_tile;
+
+  if (warp == ncw) {
+    // ===== producer =====
+    if (lane == 0) {
+      int st = 0;
+      uint32_t st_round = 0;  // how many times the stage ring wrapped
+      for (int64_t it = 0; it < n_items; ++it) {
+        const int seq = int(it / per_tile);
+        const int t = int(blockIdx.x) + seq * int(gridDim.x);
+        const int rem = int(it % per_tile);
+        const int b = rem / a.slabs, slab = rem % a.slabs;
+        if (rem == 0) {  // first item of a tile: its records and messages
+          const int mb_i = seq & 1;
+          if (seq >= 2) mbar_wait(smem_u32(&mempty_bar[mb_i]), uint32_t((seq >> 1) - 1) & 1u);
+          const int p0 = __ldg(a.tile_ptr + t), p1 = __ldg(a.tile_ptr + t + 1);
+          const int m0 = __ldg(a.tmsg_base + t) & ~1, m1 = __ldg(a.tmsg_base + t + 1);
+          const uint32_t rb = uint32_t(p1 - p0) * 16u, mb = uint32_t((m1 - m0 + 1) & ~1) * 8u;
+          const uint32_t bar = smem_u32(&mfull_bar[mb_i]);
+          const uint32_t dst = meta0 + uint32_t(mb_i) * a.meta_bytes;
+          mbar_expect_tx(bar, rb + mb);
+          bulk_g2s(dst, a.trec + p0, rb, bar);
+          if (mb) bulk_g2s(dst + a.rec_bytes, a.tmsg + m0, mb, bar);
+        }
+        if (st_round > 0) mbar_wait(smem_u32(&empty_bar[st]), (st_round - 1) & 1u);
+        const int r0 = __ldg(a.run_ptr + t), r1 = __ldg(a.run_ptr + t + 1);
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        const uint32_t dst = stage0 + uint32_t(st) * a.stage_bytes;
+        mbar_expect_tx(bar, uint32_t(r1 - r0) * run_bytes);
+        for (int r = r0; r < r1; ++r)
+          tma_load_3d(dst + uint32_t(r - r0) * run_bytes, &xmap, slab * a.slab_elems,
+                      __ldg(a.run_start + r), b, bar);
+        if (++st == ns) { st = 0; ++st_round; }
       }
-      const uint32_t lane_off = lane * 16;
-#pragma unroll 3
-      for (int e = beg; e < end; ++e) {
-        const uint64_t m = __ldg(reinterpret_cast<const unsigned long long*>(a.msg) + e);
-        const uint32_t li = static_cast<uint32_t>(m);
-        const float ww = __uint_as_float(static_cast<uint32_t>(m >> 32));
-        const uint32_t base = stage + li * row_bytes + lane_off;
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int sub = lane / LPR, l = lane % LPR;
+  int st = 0;
+  uint32_t st_round = 0;
+  for (int64_t it = 0; it < n_items; ++it) {
+    const int seq = int(it / per_tile);
+    const int t = int(blockIdx.x) + seq * int(gridDim.x);
+    const int rem = int(it % per_tile);
+    const int b = rem / a.slabs, slab = rem % a.slabs;
+    const int64_t f0 = int64_t(slab) * a.slab_elems;
+    const int64_t col = f0 + int64_t(l) * VN;
+    const bool on = col < a.feat;
+    const uint32_t stage = stage0 + uint32_t(st) * a.stage_bytes + uint32_t(l) * 16u;
+    const uint32_t recs = meta0 + uint32_t(seq & 1) * a.meta_bytes;
+    const uint32_t msgs = recs + a.rec_bytes;
+    if (rem == 0) mbar_wait(smem_u32(&mfull_bar[seq & 1]), uint32_t(seq >> 1) & 1u);
+    mbar_wait(smem_u32(&full_bar[st]), st_round & 1u);
+    const int n_rows = __ldg(a.tile_ptr + t + 1) - __ldg(a.tile_ptr + t);
+    T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
+    for (int p = warp * RPW + sub; p < n_rows; p += ncw * RPW) {
+      const int4 rec = lds_i4(recs + uint32_t(p) * 16u);  // {dst, message offset, degree, -}
+      float acc[VN];
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-          if (on[c]) {
+      for (int k = 0; k < VN; ++k) acc[k] = 0.0f;
+      for (int e0 = 0; e0 < rec.z; e0 += U) {
+        const int n = min(U, rec.z - e0);
+        const uint32_t mp = msgs + uint32_t(rec.y + e0) * 8u;
+        uint2 m[U];
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (u < n) m[u] = lds_u2(mp + u * 8u);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (u < n) v[u] = lds_v4(stage + m[u].x * slab_bytes);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (u < n) {
             float f[VN];
-            Vec16<T>::unpack(lds_v4(base + c * 512), f);
-            axpy_exact<VN>(acc[c], ww, f);
+            Vec16<T>::unpack(v[u], f);
+            axpy_exact<VN>(acc, __uint_as_float(m[u].y), f);
           }
       }
-      T* ob = static_cast<T*>(a.out) + b * a.o_bstride + d * a.ldo + f0;
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (on[c]) {
-          const int64_t cc = int64_t(c * 32 + lane) * VN;
-          stg_v4(ob + cc, finish<T, VN>(acc[c], a.bias, f0 + cc, a.relu));
-        }
+      if (on) stg_v4(ob + int64_t(rec.x) * a.ldo, finish<T, VN>(acc, a.bias, col, a.relu));
     }
-    __syncthreads();  // every warp is done with the stage before the next item overwrites it
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(smem_u32(&empty_bar[st]));
+      if (rem == per_tile - 1) mbar_arrive(smem_u32(&mempty_bar[seq & 1]));
+    }
+    if (++st == ns) { st = 0; ++st_round; }
   }
 }
 
-template <typename T, int CH>
-int launch_tiled(const TiledArgs& a, size_t smem_bytes, cudaStream_t st) {
-  auto kern = k_agg_tiled<T, CH>;
+// Developer tuning knobs (read once): GWEN_TILED_THREADS (multiple of 32, 64..1024),
+// GWEN_TILED_STAGES (2..8).
+inline int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+inline int tiled_threads_hint() {
+  static int v = env_int("GWEN_TILED_THREADS", 1024, 64, 1024) / 32 * 32;
+  return v;
+}
+inline int num_stages_hint() {
+  static int v = env_int("GWEN_TILED_STAGES", 4, 2, 8);
+  return v;
+}
+
+template <typename T, int LPR>
+int launch_tiled(const CUtensorMap& map, const TiledArgs& a, size_t smem_bytes, int threads,
+                 cudaStream_t st) {
+  auto kern = k_agg_tiled<T, LPR>;
   GWEN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_bytes)));
-  int occ = 0;
-  GWEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem_bytes));
-  if (occ < 1) return set_err(GWEN_E_NOSUPPORT, "tiled aggregate does not fit on an SM");
-  const int64_t items = a.batch * a.slabs * int64_t(a.num_tiles);
-  const int64_t grid = std::min<int64_t>(items, int64_t(sm_count()) * occ);
-  kern<<<static_cast<unsigned>(grid), 256, smem_bytes, st>>>(a);
+  const int grid = std::min(a.num_tiles, sm_count());
+  kern<<<grid, threads, smem_bytes, st>>>(map, a);
   GWEN_LAUNCH_CHECK("k_agg_tiled");
   return GWEN_OK;
 }
@@ -386,13 +459,15 @@ int launch_tiled(const TiledArgs& a, size_t smem_bytes, cudaStream_t st) {
 constexpr int kThreads = 256;
 
 struct PlanWs {
-  size_t off_keys_in, off_keys_out, off_vals_in, off_vals_out, off_rank, off_cub, cub_bytes, bytes;
+  size_t off_keys_in, off_keys_out, off_vals_in, off_vals_out, off_rank, off_usrc, off_uptr,
+      off_ulocal, off_rtmp, off_nruns, off_pos, off_cub, cub_bytes, bytes;
   int bits;
 };
 
 cudaError_t plan_ws(int64_t n_dst, int64_t m, int64_t num_tiles, PlanWs* p) {
-  (void)n_dst;
   size_t t = static_cast<size_t>(m > 0 ? m : 1);
+  size_t nt = static_cast<size_t>(num_tiles + 1);
+  size_t nd = static_cast<size_t>(n_dst + 1);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -404,10 +479,16 @@ cudaError_t plan_ws(int64_t n_dst, int64_t m, int64_t num_tiles, PlanWs* p) {
   p->off_vals_in = take(t * 4);
   p->off_vals_out = take(t * 4);
   p->off_rank = take(t * 4);
+  p->off_usrc = take(t * 4);    // distinct (tile, source) list
+  p->off_uptr = take(nt * 4);   // its per-tile offsets
+  p->off_ulocal = take(t * 4);  // stage row of each distinct source
+  p->off_rtmp = take(t * 4);    // run starts before compaction
+  p->off_nruns = take(nt * 4);
+  p->off_pos = take(nd * 4);    // message offset of every position of the processing order
   int tb = 1;
   while ((int64_t(1) << tb) < num_tiles + 1) ++tb;
   p->bits = 32 + tb;
-  size_t sort_bytes = 0, scan_bytes = 0;
+  size_t sort_bytes = 0, scan_bytes = 0, scan2_bytes = 0;
   cudaError_t err = cub::DeviceRadixSort::SortPairs(
       nullptr, sort_bytes, static_cast<const uint64_t*>(nullptr), static_cast<uint64_t*>(nullptr),
       static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<int>(t),
@@ -416,18 +497,48 @@ cudaError_t plan_ws(int64_t n_dst, int64_t m, int64_t num_tiles, PlanWs* p) {
   err = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, static_cast<int32_t*>(nullptr),
                                       static_cast<int32_t*>(nullptr), static_cast<int>(t));
   if (err != cudaSuccess) return err;
-  p->cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  err = cub::DeviceScan::ExclusiveSum(nullptr, scan2_bytes, static_cast<int32_t*>(nullptr),
+                                      static_cast<int32_t*>(nullptr),
+                                      static_cast<int>(std::max(nt, nd)));
+  if (err != cudaSuccess) return err;
+  p->cub_bytes = std::max(sort_bytes, std::max(scan_bytes, scan2_bytes));
   p->off_cub = take(p->cub_bytes);
   p->bytes = off;
   return cudaSuccess;
 }
 
-// thread per position p of the processing order: key = (tile << 32) | src for each message
-__global__ void k_plan_keys(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
-                            const int32_t* __restrict__ order,
-                            const int32_t* __restrict__ tile_ptr, int num_tiles, int64_t n_dst,
-                            uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+// degree of every position of the processing order (then exclusive-scanned into pos)
+__global__ void k_plan_deg(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ order,
+                           int64_t n_dst, int32_t* __restrict__ pos) {
   int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (p > n_dst) return;
+  if (p == n_dst) {
+    pos[p] = 0;
+    return;
+  }
+  const int64_t d = order ? order[p] : p;
+  pos[p] = rowptr[d + 1] - rowptr[d];
+}
+
+// thread per position p: row record, sort keys (tile << 32 | src) and the weight half of the
+// processing-order message list.
+__global__ void k_plan_keys(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src,
+                            const float* __restrict__ w, const int32_t* __restrict__ order,
+                            const int32_t* __restrict__ tile_ptr,
+                            const int32_t* __restrict__ pos, int num_tiles, int64_t n_dst,
+                            uint64_t* __restrict__ keys, int32_t* __restrict__ vals,
+                            int4* __restrict__ trec, uint64_t* __restrict__ tmsg,
+                            int32_t* __restrict__ tmsg_base, int32_t* __restrict__ status) {
+  int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (p <= num_tiles) {
+    const int tp = tile_ptr[p];
+    tmsg_base[p] = pos[tp];
+    if (p < num_tiles) {
+      const int tp1 = tile_ptr[p + 1];
+      atomicMax(&status[3], pos[tp1] - (pos[tp] & ~1));  // messages staged per tile
+      atomicMax(&status[4], tp1 - tp);                    // rows per tile
+    }
+  }
   if (p >= n_dst) return;
   int lo = 0, hi = num_tiles;  // last tile with tile_ptr[t] <= p
   while (hi - lo > 1) {
@@ -435,9 +546,14 @@ __global__ void k_plan_keys(const int32_t* __restrict__ rowptr, const int32_t* _
     if (tile_ptr[mid] <= p) lo = mid; else hi = mid;
   }
   const int64_t d = order ? order[p] : p;
-  for (int s = rowptr[d]; s < rowptr[d + 1]; ++s) {
-    keys[s] = (uint64_t(uint32_t(lo)) << 32) | uint32_t(src[s]);
-    vals[s] = s;
+  const int beg = rowptr[d], end = rowptr[d + 1];
+  const int q0 = pos[p];
+  trec[p] = make_int4(static_cast<int>(d), q0 - (pos[tile_ptr[lo]] & ~1), end - beg, 0);
+  for (int s = beg; s < end; ++s) {
+    const int q = q0 + (s - beg);
+    keys[q] = (uint64_t(uint32_t(lo)) << 32) | uint32_t(src[s]);
+    vals[q] = q;
+    tmsg[q] = uint64_t(__float_as_uint(w[s])) << 32;
   }
 }
 
@@ -448,41 +564,68 @@ __global__ void k_plan_heads(const uint64_t* __restrict__ keys, int64_t m,
   rank[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
 
-__global__ void k_plan_tsrc(const uint64_t* __restrict__ keys, const int32_t* __restrict__ rank,
-                            int64_t m, int num_tiles, int32_t* __restrict__ tsrc_ptr,
-                            int32_t* __restrict__ tsrc, int32_t* __restrict__ status) {
+// distinct (tile, source) pairs: usrc[u] and per-tile offsets uptr[t]
+__global__ void k_plan_unique(const uint64_t* __restrict__ keys, const int32_t* __restrict__ rank,
+                              int64_t m, int num_tiles, int32_t* __restrict__ uptr,
+                              int32_t* __restrict__ usrc) {
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i >= m) return;
   const uint64_t k = keys[i];
   const int t = static_cast<int>(k >> 32);
   const int u = rank[i] - 1;
   const bool head = i == 0 || k != keys[i - 1];
-  if (head) tsrc[u] = static_cast<int32_t>(uint32_t(k));
+  if (head) usrc[u] = static_cast<int32_t>(uint32_t(k));
   const int tp = i ? static_cast<int>(keys[i - 1] >> 32) : -1;
-  for (int tt = tp + 1; tt <= t; ++tt) tsrc_ptr[tt] = u;
-  if (i == m - 1) {
-    for (int tt = t + 1; tt <= num_tiles; ++tt) tsrc_ptr[tt] = u + 1;
-    status[0] = u + 1;
+  for (int tt = tp + 1; tt <= t; ++tt) uptr[tt] = u;
+  if (i == m - 1)
+    for (int tt = t + 1; tt <= num_tiles; ++tt) uptr[tt] = u + 1;
+}
+
+// thread per tile: cover the tile's ascending distinct sources greedily with windows of run_len
+// consecutive row ids; a source's stage row = window index * run_len + offset in the window.
+__global__ void k_plan_runs(const int32_t* __restrict__ uptr, const int32_t* __restrict__ usrc,
+                            int num_tiles, int run_len, int32_t* __restrict__ ulocal,
+                            int32_t* __restrict__ rtmp, int32_t* __restrict__ nruns,
+                            int32_t* __restrict__ status) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > num_tiles) return;
+  if (t == num_tiles) {
+    nruns[t] = 0;
+    return;
   }
+  const int u0 = uptr[t], u1 = uptr[t + 1];
+  int runs = 0;
+  int64_t cur = INT64_MIN / 2;
+  for (int u = u0; u < u1; ++u) {
+    const int s = usrc[u];
+    if (s >= cur + run_len) {
+      cur = s;
+      rtmp[u0 + runs] = s;
+      ++runs;
+    }
+    ulocal[u] = (runs - 1) * run_len + static_cast<int>(s - cur);
+  }
+  nruns[t] = runs;
+  atomicMax(&status[1], runs);
+  atomicAdd(&status[2], u1 - u0);
 }
 
-__global__ void k_plan_msg(const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals,
-                           const int32_t* __restrict__ rank,
-                           const int32_t* __restrict__ tsrc_ptr, const float* __restrict__ w,
-                           int64_t m, uint64_t* __restrict__ msg) {
-  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  if (i >= m) return;
-  const int t = static_cast<int>(keys[i] >> 32);
-  const uint32_t li = static_cast<uint32_t>(rank[i] - 1 - tsrc_ptr[t]);
-  const int32_t slot = vals[i];
-  msg[slot] = (uint64_t(__float_as_uint(w[slot])) << 32) | li;
-}
-
-__global__ void k_plan_max(const int32_t* __restrict__ tsrc_ptr, int num_tiles,
-                           int32_t* __restrict__ status) {
+__global__ void k_plan_compact(const int32_t* __restrict__ uptr, const int32_t* __restrict__ rtmp,
+                               const int32_t* __restrict__ run_ptr, int num_tiles,
+                               int32_t* __restrict__ run_start, int32_t* __restrict__ status) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tiles) return;
-  atomicMax(&status[1], tsrc_ptr[t + 1] - tsrc_ptr[t]);
+  const int r0 = run_ptr[t], r1 = run_ptr[t + 1], u0 = uptr[t];
+  for (int r = r0; r < r1; ++r) run_start[r] = rtmp[u0 + (r - r0)];
+  if (t == num_tiles - 1) status[0] = r1;
+}
+
+__global__ void k_plan_msg(const int32_t* __restrict__ vals, const int32_t* __restrict__ rank,
+                           const int32_t* __restrict__ ulocal, int64_t m,
+                           uint64_t* __restrict__ tmsg) {
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= m) return;
+  tmsg[vals[i]] |= uint64_t(uint32_t(ulocal[rank[i] - 1]));
 }
 
 __global__ void k_uniform_tiles(int64_t n_dst, int tile_rows, int64_t num_tiles,
@@ -589,14 +732,18 @@ extern "C" int gwen_tile_plan_workspace_bytes(int64_t n_dst, int64_t m, int64_t 
 
 extern "C" int gwen_tile_plan_build(const int32_t* rowptr, const int32_t* src, const float* w,
                                     const int32_t* order, const int32_t* tile_ptr,
-                                    int64_t num_tiles, int64_t n_dst, int64_t m,
-                                    int32_t* tsrc_ptr, int32_t* tsrc, uint64_t* msg,
-                                    int32_t* status, void* ws, size_t ws_bytes, void* stream) {
+                                    int64_t num_tiles, int64_t n_dst, int64_t m, int32_t run_len,
+                                    int32_t* run_ptr, int32_t* run_start, void* trec,
+                                    uint64_t* tmsg, int32_t* tmsg_base, int32_t* status, void* ws,
+                                    size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GWEN_CHECK_ARG(rowptr && src && w && tile_ptr && tsrc_ptr && tsrc && msg && status && ws,
+  GWEN_CHECK_ARG(rowptr && src && w && tile_ptr && run_ptr && run_start && trec && tmsg &&
+                     tmsg_base && status && ws,
                  "null pointer");
   GWEN_CHECK_ARG(num_tiles > 0 && num_tiles < INT32_MAX && n_dst > 0 && m > 0 && m < INT32_MAX,
                  "bad sizes");
+  GWEN_CHECK_ARG(run_len >= 1 && run_len <= 256, "run_len must be in [1, 256]");
+  GWEN_CHECK_ARG(aligned16(trec) && aligned16(tmsg), "trec / tmsg must be 16-byte aligned");
   PlanWs p;
   GWEN_CUDA(plan_ws(n_dst, m, num_tiles, &p));
   if (ws_bytes < p.bytes)
@@ -607,28 +754,46 @@ extern "C" int gwen_tile_plan_build(const int32_t* rowptr, const int32_t* src, c
   int32_t* vals_in = reinterpret_cast<int32_t*>(base + p.off_vals_in);
   int32_t* vals_out = reinterpret_cast<int32_t*>(base + p.off_vals_out);
   int32_t* rank = reinterpret_cast<int32_t*>(base + p.off_rank);
+  int32_t* usrc = reinterpret_cast<int32_t*>(base + p.off_usrc);
+  int32_t* uptr = reinterpret_cast<int32_t*>(base + p.off_uptr);
+  int32_t* ulocal = reinterpret_cast<int32_t*>(base + p.off_ulocal);
+  int32_t* rtmp = reinterpret_cast<int32_t*>(base + p.off_rtmp);
+  int32_t* nruns = reinterpret_cast<int32_t*>(base + p.off_nruns);
+  int32_t* pos = reinterpret_cast<int32_t*>(base + p.off_pos);
   void* cub_ws = base + p.off_cub;
-  GWEN_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), st));
-  const unsigned grid_n = static_cast<unsigned>(ceil_div(n_dst, kThreads));
+  const int nt = static_cast<int>(num_tiles);
+  GWEN_CUDA(cudaMemsetAsync(status, 0, 8 * sizeof(int32_t), st));
+  GWEN_CUDA(cudaMemsetAsync(tmsg + m, 0, 2 * sizeof(uint64_t), st));  // tail padding
+  const unsigned grid_n =
+      static_cast<unsigned>(ceil_div(std::max<int64_t>(n_dst, num_tiles) + 1, kThreads));
   const unsigned grid_m = static_cast<unsigned>(ceil_div(m, kThreads));
-  k_plan_keys<<<grid_n, kThreads, 0, st>>>(rowptr, src, order, tile_ptr,
-                                           static_cast<int>(num_tiles), n_dst, keys_in, vals_in);
-  GWEN_LAUNCH_CHECK("k_plan_keys");
+  const unsigned grid_t = static_cast<unsigned>(ceil_div(num_tiles + 1, kThreads));
+  k_plan_deg<<<grid_n, kThreads, 0, st>>>(rowptr, order, n_dst, pos);
+  GWEN_LAUNCH_CHECK("k_plan_deg");
   size_t cub_bytes = p.cub_bytes;
+  GWEN_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, pos, pos,
+                                          static_cast<int>(n_dst + 1), st));
+  k_plan_keys<<<grid_n, kThreads, 0, st>>>(rowptr, src, w, order, tile_ptr, pos, nt, n_dst,
+                                           keys_in, vals_in, static_cast<int4*>(trec), tmsg,
+                                           tmsg_base, status);
+  GWEN_LAUNCH_CHECK("k_plan_keys");
+  cub_bytes = p.cub_bytes;
   GWEN_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_in, keys_out, vals_in,
                                             vals_out, static_cast<int>(m), 0, p.bits, st));
   k_plan_heads<<<grid_m, kThreads, 0, st>>>(keys_out, m, rank);
   GWEN_LAUNCH_CHECK("k_plan_heads");
   cub_bytes = p.cub_bytes;
   GWEN_CUDA(cub::DeviceScan::InclusiveSum(cub_ws, cub_bytes, rank, rank, static_cast<int>(m), st));
-  k_plan_tsrc<<<grid_m, kThreads, 0, st>>>(keys_out, rank, m, static_cast<int>(num_tiles),
-                                           tsrc_ptr, tsrc, status);
-  GWEN_LAUNCH_CHECK("k_plan_tsrc");
-  k_plan_msg<<<grid_m, kThreads, 0, st>>>(keys_out, vals_out, rank, tsrc_ptr, w, m, msg);
+  k_plan_unique<<<grid_m, kThreads, 0, st>>>(keys_out, rank, m, nt, uptr, usrc);
+  GWEN_LAUNCH_CHECK("k_plan_unique");
+  k_plan_runs<<<grid_t, kThreads, 0, st>>>(uptr, usrc, nt, run_len, ulocal, rtmp, nruns, status);
+  GWEN_LAUNCH_CHECK("k_plan_runs");
+  cub_bytes = p.cub_bytes;
+  GWEN_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, nruns, run_ptr, nt + 1, st));
+  k_plan_compact<<<grid_t, kThreads, 0, st>>>(uptr, rtmp, run_ptr, nt, run_start, status);
+  GWEN_LAUNCH_CHECK("k_plan_compact");
+  k_plan_msg<<<grid_m, kThreads, 0, st>>>(vals_out, rank, ulocal, m, tmsg);
   GWEN_LAUNCH_CHECK("k_plan_msg");
-  k_plan_max<<<static_cast<unsigned>(ceil_div(num_tiles, kThreads)), kThreads, 0, st>>>(
-      tsrc_ptr, static_cast<int>(num_tiles), status);
-  GWEN_LAUNCH_CHECK("k_plan_max");
   return GWEN_OK;
 }
 
@@ -654,42 +819,67 @@ extern "C" int gwen_grid_tiles(int64_t h, int64_t w, int32_t th, int32_t tw, int
   return GWEN_OK;
 }
 
-extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const int32_t* rowptr,
-                                        const void* x, void* out, int64_t batch, int64_t n_src,
-                                        int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo,
-                                        int64_t o_bstride, int dtype, const float* bias,
-                                        int epilogue, int32_t slab_elems, void* stream) {
-  GWEN_CHECK_ARG(plan && rowptr && x && out, "null pointer");
+extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const void* x, void* out,
+                                        int64_t batch, int64_t n_src, int64_t feat, int64_t ldx,
+                                        int64_t x_bstride, int64_t ldo, int64_t o_bstride,
+                                        int dtype, const float* bias, int epilogue,
+                                        int32_t slab_elems, void* stream) {
+  GWEN_CHECK_ARG(plan && x && out, "null pointer");
   GWEN_CHECK_ARG(batch >= 0 && feat >= 0 && n_src >= 0, "negative size");
   if (batch == 0 || feat == 0 || plan->n_dst == 0) return GWEN_OK;
   GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
-  GWEN_CHECK_ARG(plan->tile_ptr && plan->tsrc_ptr && plan->tsrc && plan->msg, "incomplete plan");
+  GWEN_CHECK_ARG(plan->tile_ptr && plan->run_ptr && plan->run_start && plan->trec && plan->tmsg &&
+                     plan->tmsg_base && plan->run_len > 0 && plan->max_tile_runs > 0 &&
+                     plan->max_tile_rows > 0,
+                 "incomplete plan");
   const int esz = dtype == GWEN_F32 ? 4 : 2;
   const int vn = 16 / esz;
   if (feat % vn || ldx % vn || ldo % vn || x_bstride % vn || o_bstride % vn || !aligned16(x) ||
       !aligned16(out))
     return set_err(GWEN_E_ALIGN, "tiled aggregate needs 16-byte aligned rows (feat %% %d == 0)", vn);
-  // slab: whole 16-byte chunks, at most 64 per row (CH <= 2), and the stage must fit in smem.
-  const int64_t max_stage = 200 * 1024;
-  int64_t slab = slab_elems > 0 ? slab_elems : 32 * vn;
-  slab = std::min<int64_t>(slab, feat);
-  slab = std::min<int64_t>(slab, 64 * vn);
-  slab -= slab % vn;
-  while (slab > vn && int64_t(plan->max_tile_src) * slab * esz > max_stage) slab -= vn;
-  if (slab <= 0 || int64_t(plan->max_tile_src) * slab * esz > max_stage)
-    return set_err(GWEN_E_NOSUPPORT, "tile with %d sources does not fit in shared memory",
-                   plan->max_tile_src);
-  TiledArgs a{rowptr, plan->order, plan->tile_ptr, plan->tsrc_ptr, plan->tsrc, plan->msg, x, out,
-              bias, batch, feat, ldx, x_bstride, ldo, o_bstride, plan->num_tiles,
-              static_cast<int>(ceil_div(feat, slab)), static_cast<int>(slab),
-              (epilogue & GWEN_EPI_RELU) ? 1 : 0};
-  const size_t smem = static_cast<size_t>(plan->max_tile_src) * slab * esz;
+  // shared memory: NS >= 2 data stages (max_tile_runs * run_len rows of one slab each) + two
+  // metadata buffers (row records + messages of a tile).  slab = 8, 16 or 32 sixteen-byte
+  // chunks; slab_elems is an upper bound that is halved until two stages fit.
+  const int64_t rows = int64_t(plan->max_tile_runs) * plan->run_len;
+  const size_t rec_bytes = align_up(size_t(plan->max_tile_rows) * 16, 128);
+  const size_t meta_bytes = rec_bytes + align_up(size_t(plan->max_tile_msgs + 2) * 8, 128);
+  const size_t smem_cap = 226 * 1024;
+  auto smem_for = [&](int lpr_, int ns_) {
+    return size_t(ns_) * size_t(rows) * lpr_ * 16 + 2 * meta_bytes + 256;
+  };
+  int lpr = slab_elems > 0 ? static_cast<int>(slab_elems / vn) : 32;
+  if (lpr != 8 && lpr != 16 && lpr != 32)
+    return set_err(GWEN_E_BADARG, "slab_elems must be %d, %d or %d", 8 * vn, 16 * vn, 32 * vn);
+  while (lpr > 8 && (lpr * vn / 2 >= feat || smem_for(lpr, 2) > smem_cap)) lpr /= 2;
+  if (smem_for(lpr, 2) > smem_cap)
+    return set_err(GWEN_E_NOSUPPORT,
+                   "tile (%lld staged rows x %d B, %zu B metadata) does not fit twice in smem",
+                   (long long)rows, lpr * 16, meta_bytes);
+  int ns = 2;
+  while (ns < 8 && ns < num_stages_hint() && smem_for(lpr, ns + 1) <= smem_cap) ++ns;
+  const size_t stage_bytes = static_cast<size_t>(rows) * lpr * 16;
+  const size_t smem = smem_for(lpr, ns);
+  const int slab = lpr * vn;
+  CUtensorMap map;
+  int rc = make_tensor_map_3d(&map, x, dtype, feat, n_src, batch, ldx, x_bstride, slab,
+                              plan->run_len, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc != GWEN_OK) return rc;
+  TiledArgs a{plan->tile_ptr, plan->run_ptr, plan->run_start,
+              static_cast<const int4*>(plan->trec), plan->tmsg, plan->tmsg_base, out, bias, batch,
+              feat, ldo, o_bstride, plan->num_tiles, static_cast<int>(ceil_div(feat, slab)), slab,
+              plan->run_len, (epilogue & GWEN_EPI_RELU) ? 1 : 0,
+              static_cast<uint32_t>(stage_bytes), static_cast<uint32_t>(rec_bytes),
+              static_cast<uint32_t>(meta_bytes), ns};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool two = slab > 32 * vn;
-  if (dtype == GWEN_F32)
-    return two ? launch_tiled<float, 2>(a, smem, st) : launch_tiled<float, 1>(a, smem, st);
-  return two ? launch_tiled<__nv_bfloat16, 2>(a, smem, st)
-             : launch_tiled<__nv_bfloat16, 1>(a, smem, st);
+  const int threads = tiled_threads_hint();
+  if (dtype == GWEN_F32) {
+    if (lpr == 32) return launch_tiled<float, 32>(map, a, smem, threads, st);
+    if (lpr == 16) return launch_tiled<float, 16>(map, a, smem, threads, st);
+    return launch_tiled<float, 8>(map, a, smem, threads, st);
+  }
+  if (lpr == 32) return launch_tiled<__nv_bfloat16, 32>(map, a, smem, threads, st);
+  if (lpr == 16) return launch_tiled<__nv_bfloat16, 16>(map, a, smem, threads, st);
+  return launch_tiled<__nv_bfloat16, 8>(map, a, smem, threads, st);
 }
 
 static int dtype_ok(int dtype) {

@@ -83,12 +83,27 @@ def erdos_renyi_graph(num_nodes: int, edge_prob: float, directed: bool = False,
 class TilePlan:
     """Device arrays of a tile plan + the host struct handed to gwen_aggregate_tiled_fwd."""
 
-    def __init__(self, order, tile_ptr, tsrc_ptr, tsrc, msg, n_dst, max_tile_src, total_src):
-        self.order, self.tile_ptr, self.tsrc_ptr, self.tsrc, self.msg = order, tile_ptr, tsrc_ptr, tsrc, msg
+    def __init__(self, order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, n_dst, run_len,
+                 max_tile_runs, max_tile_rows, max_tile_msgs, total_runs, total_src):
+        self.order, self.tile_ptr, self.run_ptr, self.run_start = order, tile_ptr, run_ptr, run_start
+        self.trec, self.tmsg, self.tmsg_base = trec, tmsg, tmsg_base
         self.num_tiles = tile_ptr.numel() - 1
-        self.n_dst, self.max_tile_src, self.total_src = n_dst, max_tile_src, total_src
-        self.struct = _lib.TilePlanStruct(self.num_tiles, max_tile_src, n_dst, _ptr(order),
-                                          _ptr(tile_ptr), _ptr(tsrc_ptr), _ptr(tsrc), _ptr(msg))
+        self.n_dst, self.run_len, self.max_tile_runs = n_dst, run_len, max_tile_runs
+        self.max_tile_rows, self.max_tile_msgs = max_tile_rows, max_tile_msgs
+        self.total_runs, self.total_src = total_runs, total_src
+        self.struct = _lib.TilePlanStruct(self.num_tiles, run_len, max_tile_runs, max_tile_rows,
+                                          max_tile_msgs, 0, n_dst, _ptr(tile_ptr), _ptr(run_ptr),
+                                          _ptr(run_start), _ptr(trec), _ptr(tmsg), _ptr(tmsg_base))
+
+    @property
+    def staging_efficiency(self) -> float:
+        """distinct staged sources / staged rows (1.0 = every staged row is used)."""
+        return self.total_src / max(1, self.total_runs * self.run_len)
+
+    @property
+    def amplification(self) -> float:
+        """staged rows per destination row: the L2->SM read traffic relative to one pass."""
+        return self.total_runs * self.run_len / max(1, self.n_dst)
 
 
 class GraphCSR:
@@ -124,14 +139,18 @@ class GraphCSR:
         return self._transposed
 
     # -- tile plans ----------------------------------------------------------------------------
-    def tile_plan(self, tile: Optional[Tuple[int, ...]] = None) -> TilePlan:
-        """``tile=(th, tw)`` -> 2-D blocks of the grid (needs ``grid_shape``); ``tile=(rows,)`` ->
-        contiguous destination ranges.  Default: (8, 32) blocks on a grid, else 128-row ranges."""
+    def tile_plan(self, tile: Optional[Tuple[int, ...]] = None, run_len: Optional[int] = None) -> TilePlan:
+        """``tile=(th, tw)`` -> 2-D blocks of the grid (needs ``grid_shape``; runs of tw + 2 rows);
+        ``tile=(rows,)`` -> contiguous destination ranges.  Default: (8, 16) blocks on a grid,
+        else 128-row ranges with 32-row runs."""
         if tile is None:
-            tile = (8, 32) if self.grid_shape is not None else (128,)
+            tile = (8, 16) if self.grid_shape is not None else (128,)
         tile = tuple(int(t) for t in tile)
-        if tile in self._plans:
-            return self._plans[tile]
+        if run_len is None:
+            run_len = tile[1] + 2 if len(tile) == 2 else 32
+        key = tile + (run_len,)
+        if key in self._plans:
+            return self._plans[key]
         L, st = lib(), _stream()
         dev = self.device
         with torch.cuda.device(dev):
@@ -157,19 +176,23 @@ class GraphCSR:
             check(L.gwen_tile_plan_workspace_bytes(self.n_dst, m, nt, C.byref(need)),
                   "gwen_tile_plan_workspace_bytes")
             ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
-            tsrc_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
-            tsrc_full = torch.empty(m, dtype=torch.int32, device=dev)
-            msg = torch.empty(m, dtype=torch.int64, device=dev)
-            status = torch.zeros(2, dtype=torch.int32, device=dev)
+            run_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+            run_full = torch.empty(m, dtype=torch.int32, device=dev)
+            trec = torch.empty((self.n_dst, 4), dtype=torch.int32, device=dev)
+            tmsg = torch.empty(m + 2, dtype=torch.int64, device=dev)
+            tmsg_base = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+            status = torch.zeros(8, dtype=torch.int32, device=dev)
             check(L.gwen_tile_plan_build(_ptr(self.rowptr), _ptr(self.src), _ptr(self.w),
-                                         _ptr(order), _ptr(tile_ptr), nt, self.n_dst, m,
-                                         _ptr(tsrc_ptr), _ptr(tsrc_full), _ptr(msg), _ptr(status),
-                                         _ptr(ws), need.value, st), "gwen_tile_plan_build")
-            total, max_src = status.tolist()  # one-time sync
-            tsrc = tsrc_full[:total].clone()
-            del tsrc_full, ws
-        plan = TilePlan(order, tile_ptr, tsrc_ptr, tsrc, msg, self.n_dst, max_src, total)
-        self._plans[tile] = plan
+                                         _ptr(order), _ptr(tile_ptr), nt, self.n_dst, m, run_len,
+                                         _ptr(run_ptr), _ptr(run_full), _ptr(trec), _ptr(tmsg),
+                                         _ptr(tmsg_base), _ptr(status), _ptr(ws), need.value, st),
+                  "gwen_tile_plan_build")
+            total_runs, max_runs, total_src, max_msgs, max_rows = status.tolist()[:5]  # one-time sync
+            run_start = run_full[:total_runs].clone()
+            del run_full, ws
+        plan = TilePlan(order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, self.n_dst,
+                        run_len, max_runs, max_rows, max_msgs, total_runs, total_src)
+        self._plans[key] = plan
         return plan
 
 

@@ -142,5 +142,16 @@ class GCNConv(torch.nn.Module):
                 self._cached_graph = graph
         return gcn_conv(x, graph, self.lin.weight, self.bias, relu)
 
+    def propagate(self, edge_index, x: Tensor, add_bias: bool = True, relu: bool = False) -> Tensor:
+        """Message + aggregate only (PyG ``MessagePassing.propagate`` with GCN's message): gathers
+        ``x`` rows along the edges, scales by the symmetric norm and sums into destinations;
+        ``add_bias`` applies the layer bias in the same kernel's epilogue.  Inference-only helper
+        (no autograd) used by bench.py for BASELINE config 2."""
+        if not x.is_cuda:
+            raise RuntimeError("gwen_b200.GCNConv runs on CUDA tensors only (no CPU fallback)")
+        graph = edge_index if isinstance(edge_index, GraphCSR) else \
+            get_graph(edge_index, x.size(-2), self.add_self_loops, self.improved)
+        return ops.aggregate(graph, x.detach(), self.bias if add_bias else None, relu)
+
     def __repr__(self):
         return "%s(%d, %d)" % (self.__class__.__name__, self.in_channels, self.out_channels)

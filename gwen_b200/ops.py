@@ -49,6 +49,7 @@ def _bias32(bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = None,
               relu: bool = False, kernel: Optional[str] = None, tile=None, slab: int = 0,
+              run_len: Optional[int] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[..., i, :] = epi(sum_s w[s] * x[..., src[s], :] + bias) over the CSR of ``graph``."""
     _require_cuda(x, "x")
@@ -67,8 +68,8 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
             out = torch.empty((b, graph.n_dst, f), dtype=x3.dtype, device=x3.device)
         epi = _lib.EPI_RELU if relu else _lib.EPI_NONE
         if kernel == "tiled":
-            plan = graph.tile_plan(tile)
-            check(lib().gwen_aggregate_tiled_fwd(C.byref(plan.struct), _ptr(graph.rowptr), _ptr(x3),
+            plan = graph.tile_plan(tile, run_len)
+            check(lib().gwen_aggregate_tiled_fwd(C.byref(plan.struct), _ptr(x3),
                                                  _ptr(out), b, n_src, f, f, n_src * f, f,
                                                  graph.n_dst * f, code, _ptr(bias32), epi, slab,
                                                  _stream()), "gwen_aggregate_tiled_fwd")

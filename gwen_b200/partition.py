@@ -1,0 +1,125 @@
+"""Row-band mesh partition with a one-hop halo exchange per aggregation (multi-GPU path).
+
+No reference counterpart: GWEN's GNN trainer spawns identical replicas (``models_gnn.py:341`` has
+DistributedDataParallel commented out).  BASELINE.json's north_star asks for the mesh to be
+spatially partitioned across the GPUs of one NVSwitch box; SURVEY.md section 8(e) fixes the
+scheme restated here:
+
+* nodes are owned in contiguous id ranges (row bands of the H x W grid: node id = r*W + c);
+* a rank's local graph is the slice of the GLOBAL destination-sorted CSR for its owned rows, so
+  message order and weights (global degrees) are exactly the single-GPU ones -> partitioned
+  results are bitwise equal to unpartitioned ones;
+* local source numbering is ``[owned | halo]`` with the halo sorted by global id; before an
+  aggregation the halo rows of its input are fetched from their owners with grouped
+  send/recv (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .graph import GraphCSR
+
+__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph"]
+
+
+def band_ranges(height: int, width: int, world_size: int) -> List[range]:
+    """Owned node-id range of every rank: grid rows split as evenly as possible, in rank order."""
+    base, extra = divmod(height, world_size)
+    out, r = [], 0
+    for p in range(world_size):
+        rows = base + (1 if p < extra else 0)
+        out.append(range(r * width, (r + rows) * width))
+        r += rows
+    return out
+
+
+class LocalGraph:
+    """A rank's share of a partitioned graph: local CSR + who owns which halo row."""
+
+    def __init__(self, graph: GraphCSR, n_own: int, halo_ids: torch.Tensor, own: range):
+        self.graph, self.n_own, self.halo_ids, self.own = graph, n_own, halo_ids, own
+        self.n_halo = int(halo_ids.numel())
+
+    @property
+    def n_local(self) -> int:
+        return self.n_own + self.n_halo
+
+
+def partition_graph(global_graph: GraphCSR, own: range, grid_rows_width=None) -> LocalGraph:
+    """Slice the global CSR to the destination rows in ``own`` and renumber sources locally.
+
+    ``grid_rows_width=(rows, W)`` marks the owned band as a rows x W grid so 2-D tile plans apply.
+    One-time setup on the device (index arithmetic only, no feature data).
+    """
+    g = global_graph
+    lo, hi = own.start, own.stop
+    rp = g.rowptr[lo:hi + 1]
+    e0, e1 = int(rp[0].item()), int(rp[-1].item())
+    src_g = g.src[e0:e1].to(torch.int64)
+    remote = (src_g < lo) | (src_g >= hi)
+    halo_ids = torch.unique(src_g[remote])  # sorted ascending
+    local = torch.where(remote, (hi - lo) + torch.searchsorted(halo_ids, src_g), src_g - lo)
+    n_own = hi - lo
+    lg = GraphCSR((rp - rp[0]).contiguous(), local.to(torch.int32).contiguous(),
+                  g.w[e0:e1].contiguous(), None, None, n_own, n_own + int(halo_ids.numel()),
+                  e1 - e0, g.flags, edge_index=None, grid_shape=grid_rows_width)
+    return LocalGraph(lg, n_own, halo_ids, own)
+
+
+class HaloExchange:
+    """Fetches halo rows from their owners: ``exchange(x_local)`` fills ``x_local[..., n_own:, :]``.
+
+    Setup (collective): every rank announces the global ids it needs; each owner derives its send
+    lists.  Per call: one ``rows_gather`` (pack) per peer, one grouped batch of isend/irecv, and
+    for batched inputs one ``rows_scatter_`` (unpack) per peer.
+    """
+
+    def __init__(self, local: LocalGraph, ranges: Sequence[range], group=None):
+        self.local, self.group = local, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        dev = local.halo_ids.device
+        need = local.halo_ids.cpu().tolist()
+        all_need: List[Optional[list]] = [None] * self.world
+        dist.all_gather_object(all_need, need, group=group)
+        own = ranges[self.rank]
+        # what each peer wants from me (local row numbers), and where what I get from a peer lands
+        self.send_idx, self.recv_slice = {}, {}
+        for p in range(self.world):
+            if p == self.rank:
+                continue
+            mine = [i - own.start for i in all_need[p] if i in own]
+            if mine:
+                self.send_idx[p] = torch.tensor(mine, dtype=torch.int32, device=dev)
+            theirs = [k for k, i in enumerate(need) if i in ranges[p]]
+            if theirs:
+                assert theirs == list(range(theirs[0], theirs[-1] + 1))  # halo sorted by owner
+                self.recv_slice[p] = (local.n_own + theirs[0], len(theirs))
+
+    def exchange(self, x_local: torch.Tensor) -> torch.Tensor:
+        """x_local: [B, n_local, F] (or [n_local, F]) contiguous; rows [:n_own] valid on entry."""
+        x3 = x_local if x_local.dim() == 3 else x_local.unsqueeze(0)
+        assert x3.is_contiguous() and x3.shape[1] == self.local.n_local
+        b = x3.shape[0]
+        p2p, recv_tmp = [], {}
+        for p, idx in sorted(self.send_idx.items()):
+            buf = ops.rows_gather(x3, idx)
+            p2p.append(dist.P2POp(dist.isend, buf, p, self.group))
+        for p, (start, cnt) in sorted(self.recv_slice.items()):
+            if b == 1:
+                dst = x3[0, start:start + cnt]  # contiguous: receive straight into place
+            else:
+                dst = recv_tmp[p] = torch.empty((b, cnt, x3.shape[2]), dtype=x3.dtype, device=x3.device)
+            p2p.append(dist.P2POp(dist.irecv, dst, p, self.group))
+        if p2p:
+            for req in dist.batch_isend_irecv(p2p):
+                req.wait()
+        for p, tmp in recv_tmp.items():
+            start, cnt = self.recv_slice[p]
+            idx = torch.arange(start, start + cnt, dtype=torch.int32, device=x3.device)
+            ops.rows_scatter_(x3, idx, tmp)
+        return x_local

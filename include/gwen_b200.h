@@ -111,50 +111,64 @@ int gwen_aggregate_fwd(const int32_t* rowptr, const int32_t* src, const float* w
                        int64_t ldo, int64_t o_bstride, int dtype, const float* bias, int epilogue,
                        void* stream);
 
-/* Tiled variant: destination rows are processed in tiles whose DISTINCT source rows are staged
- * once in shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier), so a source
- * row slab crosses L2->SM once per tile instead of once per message.  The plan is built once
- * per graph from the CSR by gwen_tile_plan_build:
- *   order    int32[n_dst]        (nullable = identity) destination processing order
- *   tile_ptr int32[num_tiles+1]  tile t covers positions tile_ptr[t] .. tile_ptr[t+1] of order
- *   tsrc_ptr int32[num_tiles+1]  offsets into tsrc
- *   tsrc     int32[...]          distinct source rows of each tile, ascending
- *   msg      uint64[E']          per CSR slot: low 32 bits = index of the source inside its
- *                                tile's tsrc list, high 32 bits = the fp32 weight w[slot]
- * All arrays are caller-allocated device memory (tsrc capacity = E' is always enough).
- * The result is bitwise identical to gwen_aggregate_fwd. */
+/* Tiled variant (mesh-like graphs): destination rows are processed in tiles; the source rows a
+ * tile needs are covered by a few RUNS of run_len consecutive row ids, and each run's feature
+ * slab is brought into shared memory by ONE TMA tensor copy (cp.async.bulk.tensor, mbarrier
+ * completion), double-buffered against the reduction.  A source row slab then crosses L2->SM
+ * once per tile instead of once per message.  The plan is built once per graph from the CSR by
+ * gwen_tile_plan_build:
+ *   order     int32[n_dst]        (nullable = identity) destination processing order
+ *   tile_ptr  int32[num_tiles+1]  tile t covers positions tile_ptr[t] .. tile_ptr[t+1] of order
+ *   run_ptr   int32[num_tiles+1]  offsets into run_start
+ *   run_start int32[...]          first source row of each run (greedy cover of the tile's
+ *                                 ascending distinct sources with windows of run_len rows)
+ *   trec      int4[n_dst]         per position p of the order: {destination row, offset of its
+ *                                 first message inside the tile's staged message block, degree, 0}
+ *   tmsg      uint64[E'+2]        messages in processing order (tile-contiguous): low 32 bits =
+ *                                 staged row of the source inside its tile (run index * run_len
+ *                                 + offset), high 32 bits = the fp32 weight
+ *   tmsg_base int32[num_tiles+1]  first message of each tile in tmsg
+ * All arrays are caller-allocated device memory (run_start capacity = E' is always enough;
+ * trec and tmsg 16-byte aligned).  The result is bitwise identical to gwen_aggregate_fwd. */
 typedef struct gwen_tile_plan {
   int32_t num_tiles;
-  int32_t max_tile_src;    /* largest tsrc_ptr[t+1] - tsrc_ptr[t]; sizes the smem stage */
+  int32_t run_len;         /* rows per run = TMA box height (<= 256)                        */
+  int32_t max_tile_runs;   /* largest run_ptr[t+1] - run_ptr[t]; sizes the data stages      */
+  int32_t max_tile_rows;   /* most destination rows in a tile                               */
+  int32_t max_tile_msgs;   /* most staged messages of a tile (status[3])                    */
+  int32_t reserved;
   int64_t n_dst;
-  const int32_t* order;    /* device, nullable */
-  const int32_t* tile_ptr; /* device */
-  const int32_t* tsrc_ptr; /* device */
-  const int32_t* tsrc;     /* device */
-  const uint64_t* msg;     /* device */
+  const int32_t* tile_ptr;  /* device */
+  const int32_t* run_ptr;   /* device */
+  const int32_t* run_start; /* device */
+  const void* trec;         /* device, int4[n_dst] */
+  const uint64_t* tmsg;     /* device */
+  const int32_t* tmsg_base; /* device */
 } gwen_tile_plan;
 
 int gwen_tile_plan_workspace_bytes(int64_t n_dst, int64_t num_messages, int64_t num_tiles,
                                    size_t* bytes_out_host);
-/* status int32[2]: [0] = total distinct (tile, source) pairs = tsrc_ptr[num_tiles],
- *                  [1] = max distinct sources of any tile. */
+/* status int32[8]: [0] = total runs = run_ptr[num_tiles], [1] = max runs of any tile,
+ *   [2] = total distinct (tile, source) pairs (staging efficiency = [2] / ([0] * run_len)),
+ *   [3] = max staged messages of a tile, [4] = max destination rows of a tile. */
 int gwen_tile_plan_build(const int32_t* rowptr, const int32_t* src, const float* w,
                          const int32_t* order, const int32_t* tile_ptr, int64_t num_tiles,
-                         int64_t n_dst, int64_t num_messages, int32_t* tsrc_ptr, int32_t* tsrc,
-                         uint64_t* msg, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+                         int64_t n_dst, int64_t num_messages, int32_t run_len, int32_t* run_ptr,
+                         int32_t* run_start, void* trec, uint64_t* tmsg, int32_t* tmsg_base,
+                         int32_t* status, void* ws, size_t ws_bytes, void* stream);
 /* Tile layouts.  uniform: identity order, tile_rows destinations per tile (tile_ptr only).
  * grid: 2-D th x tw blocks of an H x W grid graph (node id r*W + c), tiles row-major; writes
  * order[H*W] and tile_ptr[ceil(H/th)*ceil(W/tw) + 1]. */
 int gwen_uniform_tiles(int64_t n_dst, int32_t tile_rows, int32_t* tile_ptr_out, void* stream);
 int gwen_grid_tiles(int64_t height, int64_t width, int32_t th, int32_t tw, int32_t* order_out,
                     int32_t* tile_ptr_out, void* stream);
-/* slab_elems: feature columns staged per work item (0 = library default); must keep
- * max_tile_src * slab_elems * sizeof(dtype) within the 227 KB shared-memory limit. */
-int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const int32_t* rowptr,
-                             const void* x, void* out, int64_t batch, int64_t n_src,
-                             int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo,
-                             int64_t o_bstride, int dtype, const float* bias, int epilogue,
-                             int32_t slab_elems, void* stream);
+/* slab_elems: feature columns staged per work item: 8, 16 or 32 sixteen-byte chunks
+ * (0 = widest that fits); two stages of max_tile_runs * run_len * slab bytes must fit in the
+ * 227 KB of shared memory, else GWEN_E_NOSUPPORT (use gwen_aggregate_fwd). */
+int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const void* x, void* out,
+                             int64_t batch, int64_t n_src, int64_t feat, int64_t ldx,
+                             int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
+                             const float* bias, int epilogue, int32_t slab_elems, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,

@@ -148,7 +148,7 @@ def test_aggregate_scalar_path_bit_exact(dev, feat):
 
 @pytest.mark.parametrize("hw,tile", [((17, 23), (8, 32)), ((40, 70), (8, 32)), ((40, 70), (4, 16)),
                                      ((33, 65), (16, 16)), ((9, 300), (2, 64))])
-@pytest.mark.parametrize("feat,slab", [(64, 0), (256, 0), (256, 256), (384, 128), (1000, 0)])
+@pytest.mark.parametrize("feat,slab", [(64, 0), (256, 0), (256, 64), (384, 128), (1000, 32), (24, 0)])
 def test_aggregate_tiled_fp32_bit_exact(dev, hw, tile, feat, slab):
     h, w = hw
     ei = orc.grid(h, w)
@@ -167,37 +167,49 @@ def test_aggregate_tiled_generic_graph(dev):
     ei, n = GRAPHS["random"]()
     g = gw.build_graph(ei.to(dev), n)
     x = wts.features((n, 128), 2)
-    out = ops.aggregate(g, x.to(dev), kernel="tiled", tile=(64,))
+    out = ops.aggregate(g, x.to(dev), kernel="tiled", tile=(64,), run_len=4)
     assert torch.equal(out.cpu(), oracle_aggregate(x, ei, n))
-    plan = g.tile_plan((64,))
-    assert plan.num_tiles == 5 and plan.max_tile_src <= n
+    plan = g.tile_plan((64,), 4)
+    assert plan.num_tiles == 5 and plan.max_tile_runs * 4 <= n + 4
 
 
 def test_tile_plan_structure(dev):
     h, w = 20, 50
     g = gw.build_graph(gw.grid(h, w, dev), h * w)
     plan = g.tile_plan((8, 32))
+    assert plan.run_len == 34
     order = plan.order.cpu().numpy()
     assert sorted(order.tolist()) == list(range(h * w))
     tp = plan.tile_ptr.cpu().numpy()
     assert plan.num_tiles == 3 * 2 and tp[0] == 0 and tp[-1] == h * w
     first = order[tp[0]:tp[1]]
     assert set(first.tolist()) == {r * w + c for r in range(8) for c in range(32)}
-    tsp = plan.tsrc_ptr.cpu().numpy()
-    ts = plan.tsrc.cpu().numpy()
-    assert set(ts[tsp[0]:tsp[1]].tolist()) == {r * w + c for r in range(9) for c in range(33)}
-    assert plan.max_tile_src == 10 * 34
-    # every message points at its own source inside the tile's list
-    msg = plan.msg.cpu().numpy().view(np.uint64)
-    li = (msg & np.uint64(0xFFFFFFFF)).astype(np.int64)
-    wbits = (msg >> np.uint64(32)).astype(np.uint32).view(np.float32)
-    assert np.array_equal(wbits, g.w.cpu().numpy())
-    rowptr, src = g.rowptr.cpu().numpy(), g.src.cpu().numpy()
+    rp = plan.run_ptr.cpu().numpy()
+    rs = plan.run_start.cpu().numpy()
+    assert rs[rp[0]:rp[1]].tolist() == [r * w for r in range(9)]          # tile (0,0): 9 row segments
+    assert rs[rp[1]:rp[2]].tolist() == [r * w + 31 for r in range(9)]     # tile (0,1): cols 31..49
+    assert plan.max_tile_runs == 10
+    assert 0.7 < plan.staging_efficiency <= 1.0          # border tiles stage 34-row boxes for 19-col runs
+    # records + messages in processing order point at the right destination / source / weight
+    rec = plan.trec.cpu().numpy()
+    base = plan.tmsg_base.cpu().numpy()
+    tm = plan.tmsg.cpu().numpy().view(np.uint64)
+    li = (tm & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    wbits = (tm >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    rowptr, src, wcsr = g.rowptr.cpu().numpy(), g.src.cpu().numpy(), g.w.cpu().numpy()
+    assert base[-1] == g.num_messages
+    assert plan.max_tile_rows == 8 * 32 and plan.max_tile_msgs >= 9 * 8 * 32 - 200
     for t in range(plan.num_tiles):
+        m0 = base[t] & ~1
         for p in range(tp[t], tp[t + 1]):
-            d = order[p]
-            for s in range(rowptr[d], rowptr[d + 1]):
-                assert ts[tsp[t] + li[s]] == src[s]
+            d, moff, deg, _ = rec[p]
+            assert d == order[p] and deg == rowptr[d + 1] - rowptr[d]
+            for k in range(deg):
+                q, s_ = m0 + moff + k, rowptr[d] + k
+                run, off = divmod(li[q], plan.run_len)
+                assert run < rp[t + 1] - rp[t]
+                assert rs[rp[t] + run] + off == src[s_]
+                assert wbits[q] == wcsr[s_]
 
 
 @pytest.mark.parametrize("kernel", ["rows", "tiled"])
