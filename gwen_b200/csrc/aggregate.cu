@@ -94,8 +94,33 @@ template <typename T, int N>
 __device__ __forceinline__ uint4 finish(float* acc, const float* __restrict__ bias, int64_t col,
                                         int relu) {
   if (bias) {
+    float bv[N];
+    if constexpr (N == 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __ldg(bias + col + k));
+      for (int k = 0; k < N; k += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col + k));
+        bv[k] = b4.x; bv[k + 1] = b4.y; bv[k + 2] = b4.z; bv[k + 3] = b4.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], bv[k]);
+  }
+  if (relu) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = fmaxf(acc[k], 0.0f);
+  }
+  return Vec16<T>::pack(acc);
+}
+
+// Same epilogue with the bias already in registers (hoisted out of the row loop).
+template <typename T, int N>
+__device__ __forceinline__ uint4 finish_reg(float* acc, const float* bv, bool has_bias, int relu) {
+  if (has_bias) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], bv[k]);
   }
   if (relu) {
 #pragma unroll
@@ -302,12 +327,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 //     rows out of shared memory -- record -> messages (broadcast LDS.64) -> source slabs
 //     (LDS.128) -> fp32 accumulate in CSR order -> STG.128 -- then one lane per warp arrives on
 //     empty[stage].  No block-wide barrier: a fast warp runs up to NS-1 items ahead.
-template <typename T, int LPR>
-__global__ void __launch_bounds__(1024, 1) k_agg_tiled(const __grid_constant__ CUtensorMap xmap,
-                                                       TiledArgs a) {
+template <typename T, int LPR, int U>  // U = messages in flight per row
+__global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CUtensorMap xmap,
+                                                      TiledArgs a) {
   constexpr int VN = Vec16<T>::N;
   constexpr int RPW = 32 / LPR;
-  constexpr int U = 5;      // messages in flight per row
   constexpr int MAXS = 8;   // most data stages
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAXS], empty_bar[MAXS], mfull_bar[2], mempty_bar[2];
@@ -391,6 +415,9 @@ __global__ void __launch_bounds__(1024, 1) k_agg_tiled(const __grid_constant__ C
     mbar_wait(smem_u32(&full_bar[st]), st_round & 1u);
     const int n_rows = __ldg(a.tile_ptr + t + 1) - __ldg(a.tile_ptr + t);
     T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
+    float bv[VN];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) bv[k] = (a.bias && on) ? __ldg(a.bias + col + k) : 0.0f;
     for (int p = warp * RPW + sub; p < n_rows; p += ncw * RPW) {
       const int4 rec = lds_i4(recs + uint32_t(p) * 16u);  // {dst, message offset, degree, -}
       float acc[VN];
@@ -415,7 +442,8 @@ __global__ void __launch_bounds__(1024, 1) k_agg_tiled(const __grid_constant__ C
             axpy_exact<VN>(acc, __uint_as_float(m[u].y), f);
           }
       }
-      if (on) stg_v4(ob + int64_t(rec.x) * a.ldo, finish<T, VN>(acc, a.bias, col, a.relu));
+      if (on)
+        stg_v4(ob + int64_t(rec.x) * a.ldo, finish_reg<T, VN>(acc, bv, a.bias != nullptr, a.relu));
     }
     __syncwarp();
     if (lane == 0) {
@@ -426,8 +454,8 @@ __global__ void __launch_bounds__(1024, 1) k_agg_tiled(const __grid_constant__ C
   }
 }
 
-// Developer tuning knobs (read once): GWEN_TILED_THREADS (multiple of 32, 64..1024),
-// GWEN_TILED_STAGES (2..8).
+// Developer tuning knobs (read once): GWEN_TILED_THREADS (multiple of 32, 64..512),
+// GWEN_TILED_STAGES (2..8), GWEN_TILED_U (5 or 9 messages in flight per row).
 inline int env_int(const char* name, int dflt, int lo, int hi) {
   const char* v = getenv(name);
   if (!v) return dflt;
@@ -435,7 +463,7 @@ inline int env_int(const char* name, int dflt, int lo, int hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
 inline int tiled_threads_hint() {
-  static int v = env_int("GWEN_TILED_THREADS", 1024, 64, 1024) / 32 * 32;
+  static int v = env_int("GWEN_TILED_THREADS", 512, 64, 512) / 32 * 32;
   return v;
 }
 inline int num_stages_hint() {
@@ -443,16 +471,24 @@ inline int num_stages_hint() {
   return v;
 }
 
-template <typename T, int LPR>
-int launch_tiled(const CUtensorMap& map, const TiledArgs& a, size_t smem_bytes, int threads,
-                 cudaStream_t st) {
-  auto kern = k_agg_tiled<T, LPR>;
+template <typename T, int LPR, int U>
+int launch_tiled_u(const CUtensorMap& map, const TiledArgs& a, size_t smem_bytes, int threads,
+                   cudaStream_t st) {
+  auto kern = k_agg_tiled<T, LPR, U>;
   GWEN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_bytes)));
   const int grid = std::min(a.num_tiles, sm_count());
   kern<<<grid, threads, smem_bytes, st>>>(map, a);
   GWEN_LAUNCH_CHECK("k_agg_tiled");
   return GWEN_OK;
+}
+
+template <typename T, int LPR>
+int launch_tiled(const CUtensorMap& map, const TiledArgs& a, size_t smem_bytes, int threads,
+                 cudaStream_t st) {
+  static const int u = env_int("GWEN_TILED_U", 9, 1, 9);
+  return u >= 9 ? launch_tiled_u<T, LPR, 9>(map, a, smem_bytes, threads, st)
+                : launch_tiled_u<T, LPR, 5>(map, a, smem_bytes, threads, st);
 }
 
 // ---- tile plan --------------------------------------------------------------------------------

@@ -73,7 +73,7 @@ def main():
             if kern == "tiled":
                 pl = g.tile_plan(tile)
                 extra = {"amp": round(pl.amplification, 3), "runs": pl.max_tile_runs, "rl": pl.run_len}
-            extra["env"] = os.environ.get("GWEN_TILED_THREADS", "") + "/" + os.environ.get("GWEN_TILED_STAGES", "")
+            extra["env"] = "/".join(os.environ.get(k, "") for k in ("GWEN_TILED_THREADS", "GWEN_TILED_STAGES", "GWEN_TILED_U"))
             print(json.dumps({"kernel": kern, "tile": tile, "slab": slab, **extra, "us_med": round(med, 1),
                               "us_min": round(mn, 1), "GBs_alg": round(alg / med / 1e3, 1),
                               "bitwise_ok": ok}), flush=True)
