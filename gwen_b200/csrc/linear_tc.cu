@@ -1,14 +1,241 @@
-// K2 (tensor-core path) -- placeholder until the tcgen05 kernel lands: reports "not supported"
-// so gwen_linear_fwd takes the CUDA-core GEMM.
+// K2 (tensor-core path): y = epi(x W^T + bias) for bf16 on the 5th-generation tensor cores.
+//
+//   x : [M, K] bf16 row-major (K-major A operand)      W : [N, K] bf16 row-major (K-major B)
+//   y : [M, N] bf16, fp32 accumulation in TMEM
+//
+// One CTA computes a 128 x BN output tile (BN = 32..256).  Warp roles (192 threads):
+//   warp 0 (one lane)  TMA producer: per 64-wide K block one cp.async.bulk.tensor for the A tile
+//                      (128 x 64) and one for the B tile (BN x 64), SWIZZLE_128B, landing on
+//                      full[stage]; waits empty[stage] before reusing a stage.
+//   warp 1             allocates BN TMEM columns; one lane issues 4 x tcgen05.mma (M=128, N=BN,
+//                      K=16, kind::f16) per K block from shared-memory descriptors and commits to
+//                      empty[stage]; the last commit also arrives on tmem_full.
+//   warps 2..5         epilogue: tcgen05.ld their 32 TMEM lanes (= 32 output rows) 32 columns at
+//                      a time, add bias, ReLU, round to bf16, 16-byte global stores.
+// 1-2 CTAs are resident per SM (shared memory / TMEM columns permitting) so one CTA's epilogue
+// overlaps another's main loop.  Rows beyond M and columns of K beyond the tensor are zero-filled
+// by TMA; stores are masked.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace gwen {
-int linear_tc_supported(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, const void*,
-                        const void*, const void*) {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;        // bf16 elements per K block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kTcThreads = 192;
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 B
+// apart (SBO), LBO unused (=1) for swizzled K-major, descriptor version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);         // start address, bits [0,14)
+  d |= uint64_t(1) << 16;                         // leading byte offset (ignored), bits [16,30)
+  d |= uint64_t(1024 >> 4) << 32;                 // stride byte offset, bits [32,46)
+  d |= uint64_t(1) << 46;                         // version = 1
+  d |= uint64_t(2) << 61;                         // layout type: SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = bn.
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcArgs {
+  __nv_bfloat16* y;
+  const float* bias;
+  int64_t m, ldy;
+  int n, k_blocks, bn, stages, relu;
+};
+
+__global__ void __launch_bounds__(kTcThreads) k_linear_tc(const __grid_constant__ CUtensorMap amap,
+                                                          const __grid_constant__ CUtensorMap bmap,
+                                                          TcArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024-B aligned
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = uint32_t(g.bn) * BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = g.n / g.bn;
+  const int64_t m0 = (int64_t(blockIdx.x) / n_tiles) * BM;
+  const int n0 = int(blockIdx.x % n_tiles) * g.bn;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap);
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // TMEM allocation (power of two >= 32 columns), owned by warp 1
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(uint32_t(g.bn < 32 ? 32 : g.bn))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < g.k_blocks; ++kb) {
+        const int s = kb % g.stages;
+        const uint32_t round = uint32_t(kb / g.stages);
+        if (round > 0) mbar_wait(smem_u32(&empty_bar[s]), (round - 1) & 1u);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t dst = tiles + uint32_t(s) * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
+        tma_load_3d(dst, &amap, kb * BK, int(m0), 0, bar);
+        tma_load_3d(dst + a_bytes, &bmap, kb * BK, n0, 0, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc(g.bn);
+      for (int kb = 0; kb < g.k_blocks; ++kb) {
+        const int s = kb % g.stages;
+        mbar_wait(smem_u32(&full_bar[s]), uint32_t(kb / g.stages) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = tiles + uint32_t(s) * stage_bytes;
+        const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(a_addr + a_bytes);
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk)  // +32 bytes (>>4 = 2) per UMMA_K inside the row
+          umma_f16(tmem_d, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+                   (kb | kk) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[s]));  // frees the stage when these MMAs retire
+      }
+      umma_commit(smem_u32(&tmem_full_bar));   // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int64_t row = m0 + q * 32 + lane;
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    __nv_bfloat16* yrow = g.y + row * g.ldy + n0;
+    for (int c = 0; c < g.bn; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c), r);
+      if (row < g.m) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            f[t] = __uint_as_float(r[j + t]);
+            if (g.bias) f[t] += __ldg(g.bias + n0 + c + j + t);
+            if (g.relu) f[t] = fmaxf(f[t], 0.0f);
+          }
+          uint4 o;
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]);
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(f[2], f[3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]);
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(f[6], f[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&p0);
+          o.y = *reinterpret_cast<uint32_t*>(&p1);
+          o.z = *reinterpret_cast<uint32_t*>(&p2);
+          o.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(yrow + c + j) = o;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                 "r"(uint32_t(g.bn < 32 ? 32 : g.bn))
+                 : "memory");
+  }
+}
+
+int pick_bn(int64_t n) {
+  for (int bn : {256, 128, 64, 32})
+    if (n % bn == 0) return bn;
   return 0;
 }
-int linear_tc_fwd_bf16(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t,
-                       int64_t, int64_t, const float*, int, cudaStream_t) {
-  return set_err(GWEN_E_NOSUPPORT, "tcgen05 GEMM not built");
+
+}  // namespace
+
+int linear_tc_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                        const void* x, const void* w, const void* y) {
+  static const bool disabled = getenv("GWEN_DISABLE_TC") != nullptr;
+  if (disabled) return 0;
+  if (m < 1 || k < 8 || n_out < 32 || n_out > INT32_MAX || m > INT32_MAX) return 0;
+  if (k % 8 || ldx % 8 || ldw % 8 || ldy % 8) return 0;  // 16-byte pitches for TMA / v4 stores
+  if (!aligned16(x) || !aligned16(w) || !aligned16(y)) return 0;
+  return pick_bn(n_out) != 0;
 }
+
+int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
+                       int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
+                       cudaStream_t st) {
+  const int bn = pick_bn(n_out);
+  if (!bn) return set_err(GWEN_E_NOSUPPORT, "tcgen05 GEMM needs n_out %% 32 == 0");
+  CUtensorMap amap, bmap;
+  int rc = make_tensor_map_3d(&amap, x, GWEN_BF16, k, m, 1, ldx, 0, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  rc = make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  const int k_blocks = static_cast<int>(ceil_div(k, BK));
+  const size_t stage_bytes = size_t(BM + bn) * BK * 2;
+  // up to 4 stages, at most ~100 KB so that two CTAs share an SM
+  int stages = static_cast<int>(std::min<int64_t>(std::min<int64_t>(4, k_blocks), (100 * 1024) / stage_bytes));
+  if (stages < 1) stages = 1;
+  if (stages < 2 && k_blocks > 1) stages = 2;
+  const size_t smem = stages * stage_bytes + 1024;
+  TcArgs g{static_cast<__nv_bfloat16*>(y), bias, m, ldy, static_cast<int>(n_out), k_blocks, bn,
+           stages, relu};
+  GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  const int64_t grid = ceil_div(m, BM) * (n_out / bn);
+  if (grid > INT32_MAX) return set_err(GWEN_E_NOSUPPORT, "GEMM grid too large");
+  k_linear_tc<<<static_cast<unsigned>(grid), kTcThreads, smem, st>>>(amap, bmap, g);
+  GWEN_LAUNCH_CHECK("k_linear_tc");
+  return GWEN_OK;
+}
+
 }  // namespace gwen

@@ -250,13 +250,22 @@ def test_linear_fp32(dev, m, k, n):
     assert nmax(y2, x.double() @ w.double().t()) <= FP32_TOL
 
 
-@pytest.mark.parametrize("m,k,n", [(300, 64, 1024), (1000, 1024, 512), (640, 512, 256), (130, 40, 24)])
+@pytest.mark.parametrize("m,k,n", [(300, 64, 1024), (1000, 1024, 512), (640, 512, 256), (130, 40, 24),
+                                   (257, 72, 96), (643, 1024, 64), (5, 256, 512), (4096, 256, 256),
+                                   (20000, 128, 128)])
 def test_linear_bf16(dev, m, k, n):
+    """bf16 projection (tcgen05 path when K % 8 == 0 and N % 32 == 0, CUDA-core path otherwise)
+    against a plain fp64 reference of the same bf16-rounded operands."""
     x, w, b = wts.features((m, k), 1).bfloat16(), wts.glorot(n, k, 2).bfloat16(), wts.small_bias(n, 3)
     ref = x.double() @ w.double().t() + b.double()
     y = ops.linear(x.to(dev), w.to(dev), b.to(dev))
     assert y.dtype == torch.bfloat16
     assert nmax(y, ref) <= 1e-2                           # one bf16 rounding of an fp32-accumulated sum
+    # elementwise: |y - ref| <= 1 bf16 ulp of |ref| + fp32 accumulation slack
+    err = (y.double().cpu() - ref).abs()
+    assert torch.all(err <= ref.abs() * 2.0 ** -7 + 1e-3)
+    yr = ops.linear(x.to(dev), w.to(dev), b.to(dev), relu=True)
+    assert torch.equal(yr, torch.relu(y))
 
 
 @pytest.mark.parametrize("m,k,n", [(300, 64, 128), (5000, 96, 40), (129, 256, 512)])
