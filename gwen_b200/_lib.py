@@ -68,6 +68,7 @@ _p, _i64, _i32, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, 
 # name -> (restype, argtypes); every symbol include/gwen_b200.h declares.
 PROTOTYPES = {
     "gwen_version": (_int, []),
+    "gwen_set_sm_reserve": (_int, [_int]),
     "gwen_last_error": (C.c_char_p, []),
     "gwen_graph_workspace_bytes": (_int, [_i64, _i64, _u32, C.POINTER(_sz)]),
     "gwen_graph_build": (_int, [_p, _i64, _i64, _u32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
@@ -82,7 +83,8 @@ PROTOTYPES = {
     "gwen_uniform_tiles": (_int, [_i64, _i32, _p, _p]),
     "gwen_grid_tiles": (_int, [_i64, _i64, _i32, _i32, _p, _p, _p]),
     "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _i64, _i64, _i64,
-                                        _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _p]),
+                                        _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _i32, _i32,
+                                        _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,

@@ -84,10 +84,15 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
 
 __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
-template <int N>
+// fp32 data: unfused mul.rn + add.rn, so the sum equals the CPU scatter_add_ order bitwise.
+// bf16 data: the result is rounded to bf16 anyway (tolerance-checked), so one FFMA per element.
+template <typename T, int N>
 __device__ __forceinline__ void axpy_exact(float* acc, float w, const float* v) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) acc[k] = __fadd_rn(acc[k], __fmul_rn(w, v[k]));
+  for (int k = 0; k < N; ++k) {
+    if constexpr (sizeof(T) == 4) acc[k] = __fadd_rn(acc[k], __fmul_rn(w, v[k]));
+    else acc[k] = fmaf(w, v[k], acc[k]);
+  }
 }
 
 template <typename T, int N>
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(256) k_agg_rows(AggArgs a, int64_t row_groups,
         if (on[c]) {
           float f[VN];
           Vec16<T>::unpack(v[u][c], f);
-          axpy_exact<VN>(acc[c], ww[u], f);
+          axpy_exact<T, VN>(acc[c], ww[u], f);
         }
   }
   for (; e < end; ++e) {
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(256) k_agg_rows(AggArgs a, int64_t row_groups,
       if (on[c]) {
         float f[VN];
         Vec16<T>::unpack(v[c], f);
-        axpy_exact<VN>(acc[c], ww, f);
+        axpy_exact<T, VN>(acc[c], ww, f);
       }
   }
   T* ob = static_cast<T*>(a.out) + b * a.o_bstride + d * a.ldo;
@@ -288,7 +293,7 @@ struct TiledArgs {
   void* out;
   const float* bias;
   int64_t batch, feat, ldo, o_bstride;
-  int num_tiles, slabs, slab_elems, run_len, relu;
+  int num_tiles, tile_begin, slabs, slab_elems, run_len, relu;
   uint32_t stage_bytes;  // one data stage = max_tile_runs * run_len * slab bytes
   uint32_t rec_bytes;    // one metadata buffer: records, then messages
   uint32_t meta_bytes;
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
       uint32_t st_round = 0;  // how many times the stage ring wrapped
       for (int64_t it = 0; it < n_items; ++it) {
         const int seq = int(it / per_tile);
-        const int t = int(blockIdx.x) + seq * int(gridDim.x);
+        const int t = a.tile_begin + int(blockIdx.x) + seq * int(gridDim.x);
         const int rem = int(it % per_tile);
         const int b = rem / a.slabs, slab = rem % a.slabs;
         if (rem == 0) {  // first item of a tile: its records and messages
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
   uint32_t st_round = 0;
   for (int64_t it = 0; it < n_items; ++it) {
     const int seq = int(it / per_tile);
-    const int t = int(blockIdx.x) + seq * int(gridDim.x);
+    const int t = a.tile_begin + int(blockIdx.x) + seq * int(gridDim.x);
     const int rem = int(it % per_tile);
     const int b = rem / a.slabs, slab = rem % a.slabs;
     const int64_t f0 = int64_t(slab) * a.slab_elems;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
           if (u < n) {
             float f[VN];
             Vec16<T>::unpack(v[u], f);
-            axpy_exact<VN>(acc, __uint_as_float(m[u].y), f);
+            axpy_exact<T, VN>(acc, __uint_as_float(m[u].y), f);
           }
       }
       if (on)
@@ -477,7 +482,7 @@ int launch_tiled_u(const CUtensorMap& map, const TiledArgs& a, size_t smem_bytes
   auto kern = k_agg_tiled<T, LPR, U>;
   GWEN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem_bytes)));
-  const int grid = std::min(a.num_tiles, sm_count());
+  const int grid = std::min(a.num_tiles, std::max(1, sm_count() - sm_reserve()));
   kern<<<grid, threads, smem_bytes, st>>>(map, a);
   GWEN_LAUNCH_CHECK("k_agg_tiled");
   return GWEN_OK;
@@ -859,8 +864,15 @@ extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const void* 
                                         int64_t batch, int64_t n_src, int64_t feat, int64_t ldx,
                                         int64_t x_bstride, int64_t ldo, int64_t o_bstride,
                                         int dtype, const float* bias, int epilogue,
-                                        int32_t slab_elems, void* stream) {
+                                        int32_t slab_elems, int32_t tile_begin,
+                                        int32_t tile_count, void* stream) {
   GWEN_CHECK_ARG(plan && x && out, "null pointer");
+  GWEN_CHECK_ARG(tile_begin >= 0 && tile_count >= 0 && tile_begin + tile_count <= plan->num_tiles,
+                 "tile range outside the plan");
+  if (tile_count == 0) {
+    if (tile_begin != 0) return GWEN_OK;  // empty range
+    tile_count = plan->num_tiles;
+  }
   GWEN_CHECK_ARG(batch >= 0 && feat >= 0 && n_src >= 0, "negative size");
   if (batch == 0 || feat == 0 || plan->n_dst == 0) return GWEN_OK;
   GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
@@ -902,7 +914,7 @@ extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const void* 
   if (rc != GWEN_OK) return rc;
   TiledArgs a{plan->tile_ptr, plan->run_ptr, plan->run_start,
               static_cast<const int4*>(plan->trec), plan->tmsg, plan->tmsg_base, out, bias, batch,
-              feat, ldo, o_bstride, plan->num_tiles, static_cast<int>(ceil_div(feat, slab)), slab,
+              feat, ldo, o_bstride, tile_count, tile_begin, static_cast<int>(ceil_div(feat, slab)), slab,
               plan->run_len, (epilogue & GWEN_EPI_RELU) ? 1 : 0,
               static_cast<uint32_t>(stage_bytes), static_cast<uint32_t>(rec_bytes),
               static_cast<uint32_t>(meta_bytes), ns};

@@ -31,7 +31,15 @@ int sm_count() {
   return cached;
 }
 
+static int g_sm_reserve = 0;
+int sm_reserve() { return g_sm_reserve; }
+
 }  // namespace gwen
 
+extern "C" int gwen_set_sm_reserve(int n) {
+  int old = gwen::g_sm_reserve;
+  gwen::g_sm_reserve = n < 0 ? 0 : n;
+  return old;
+}
 extern "C" int gwen_version(void) { return GWEN_ABI_VERSION; }
 extern "C" const char* gwen_last_error(void) { return gwen::err_buf(); }

@@ -42,6 +42,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();  // cached multiProcessorCount of the current device (148 on B200)
+int sm_reserve();  // SMs the persistent kernels leave free (gwen_set_sm_reserve)
 
 template <typename T>
 struct DType;

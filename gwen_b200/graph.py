@@ -139,6 +139,16 @@ class GraphCSR:
         return self._transposed
 
     # -- tile plans ----------------------------------------------------------------------------
+    def tile_plan_from(self, order: Optional[torch.Tensor], tile_ptr: torch.Tensor, run_len: int,
+                       key: Tuple) -> TilePlan:
+        """Plan for an explicit tile layout: ``order`` int32[n_dst] (or None) and ``tile_ptr``
+        int32[num_tiles + 1] on this graph's device; memoised under ``key``."""
+        if key in self._plans:
+            return self._plans[key]
+        plan = self._build_plan(order, tile_ptr, run_len)
+        self._plans[key] = plan
+        return plan
+
     def tile_plan(self, tile: Optional[Tuple[int, ...]] = None, run_len: Optional[int] = None) -> TilePlan:
         """``tile=(th, tw)`` -> 2-D blocks of the grid (needs ``grid_shape``; runs of tw + 2 rows);
         ``tile=(rows,)`` -> contiguous destination ranges.  Default: (8, 16) blocks on a grid,
@@ -171,6 +181,15 @@ class GraphCSR:
                 tile_ptr = torch.empty(nt + 1, dtype=torch.int32, device=dev)
                 check(L.gwen_uniform_tiles(self.n_dst, rows, _ptr(tile_ptr), st),
                       "gwen_uniform_tiles")
+        plan = self._build_plan(order, tile_ptr, run_len)
+        self._plans[key] = plan
+        return plan
+
+    def _build_plan(self, order, tile_ptr, run_len: int) -> TilePlan:
+        L, st = lib(), _stream()
+        dev = self.device
+        nt = tile_ptr.numel() - 1
+        with torch.cuda.device(dev):
             m = self.num_messages
             need = C.c_size_t()
             check(L.gwen_tile_plan_workspace_bytes(self.n_dst, m, nt, C.byref(need)),
@@ -190,10 +209,8 @@ class GraphCSR:
             total_runs, max_runs, total_src, max_msgs, max_rows = status.tolist()[:5]  # one-time sync
             run_start = run_full[:total_runs].clone()
             del run_full, ws
-        plan = TilePlan(order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, self.n_dst,
+        return TilePlan(order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, self.n_dst,
                         run_len, max_runs, max_rows, max_msgs, total_runs, total_src)
-        self._plans[key] = plan
-        return plan
 
 
 def _build(edge_index: torch.Tensor, num_nodes: int, flags: int,

@@ -49,9 +49,11 @@ def _bias32(bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = None,
               relu: bool = False, kernel: Optional[str] = None, tile=None, slab: int = 0,
-              run_len: Optional[int] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[..., i, :] = epi(sum_s w[s] * x[..., src[s], :] + bias) over the CSR of ``graph``."""
+              run_len: Optional[int] = None, out: Optional[torch.Tensor] = None,
+              tile_range: Optional[tuple] = None, plan: Optional[TilePlan] = None) -> torch.Tensor:
+    """out[..., i, :] = epi(sum_s w[s] * x[..., src[s], :] + bias) over the CSR of ``graph``.
+    ``tile_range=(begin, count)`` (tiled kernel only) restricts the launch to those tiles of the
+    plan; the other rows of ``out`` are left untouched."""
     _require_cuda(x, "x")
     x3, lead = _as_3d(x)
     b, n_src, f = x3.shape
@@ -68,10 +70,13 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
             out = torch.empty((b, graph.n_dst, f), dtype=x3.dtype, device=x3.device)
         epi = _lib.EPI_RELU if relu else _lib.EPI_NONE
         if kernel == "tiled":
-            plan = graph.tile_plan(tile, run_len)
+            if plan is None:
+                plan = graph.tile_plan(tile, run_len)
             check(lib().gwen_aggregate_tiled_fwd(C.byref(plan.struct), _ptr(x3),
                                                  _ptr(out), b, n_src, f, f, n_src * f, f,
                                                  graph.n_dst * f, code, _ptr(bias32), epi, slab,
+                                                 tile_range[0] if tile_range else 0,
+                                                 tile_range[1] if tile_range else 0,
                                                  _stream()), "gwen_aggregate_tiled_fwd")
         elif kernel == "rows":
             check(lib().gwen_aggregate_fwd(_ptr(graph.rowptr), _ptr(graph.src), _ptr(graph.w),

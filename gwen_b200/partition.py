@@ -23,7 +23,7 @@ import torch.distributed as dist
 from . import ops
 from .graph import GraphCSR
 
-__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph"]
+__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator"]
 
 
 def band_ranges(height: int, width: int, world_size: int) -> List[range]:
@@ -123,3 +123,77 @@ class HaloExchange:
             idx = torch.arange(start, start + cnt, dtype=torch.int32, device=x3.device)
             ops.rows_scatter_(x3, idx, tmp)
         return x_local
+
+
+class BandAggregator:
+    """Aggregation over a rank's row band with the halo exchange hidden behind interior work.
+
+    Only the first and last tile rows of the band read halo rows.  The band's tile plan lists
+    those boundary tiles first, so a step is: (1) halo exchange issued on a side stream,
+    (2) ONE launch over the interior tiles on the caller's stream -- a few SMs are left free
+    (``sm_reserve``) so the pack and NCCL kernels can run beside the persistent kernel --
+    (3) the caller's stream waits for the exchange and runs ONE launch over the boundary tiles.
+    """
+
+    def __init__(self, local: LocalGraph, hx: HaloExchange, tile=(8, 16), sm_reserve: int = 8,
+                 strip_width: int = 32):
+        if local.graph.grid_shape is None:
+            raise RuntimeError("BandAggregator needs a grid-shaped band (grid_rows_width)")
+        self.local, self.hx, self.tile, self.sm_reserve = local, hx, tuple(tile), sm_reserve
+        g = local.graph
+        rows, width = g.grid_shape
+        dev = g.device
+        th, tw = self.tile
+
+        def region(r0, r1, rth, rtw):
+            """(order, tile sizes) of the rth x rtw tiles covering grid rows [r0, r1), row-major."""
+            if r1 <= r0:
+                return (torch.empty(0, dtype=torch.int64, device=dev),) * 2
+            r = torch.arange(r0, r1, device=dev).view(-1, 1).expand(-1, width).reshape(-1)
+            c = torch.arange(width, device=dev).repeat(r1 - r0)
+            tcols = -(-width // rtw)
+            tid = ((r - r0) // rth) * tcols + c // rtw
+            key = tid * (rth * rtw) + ((r - r0) % rth) * rtw + c % rtw
+            perm = torch.argsort(key)
+            return (r * width + c)[perm], torch.bincount(tid)
+
+        # boundary: the first and last grid row of the band as 1 x strip_width strips (the only
+        # destinations whose sources include halo rows); interior: everything between them.
+        top, top_sz = region(0, min(1, rows), 1, strip_width)
+        bot, bot_sz = region(max(rows - 1, 1), rows, 1, strip_width)
+        mid, mid_sz = region(1, rows - 1, th, tw)
+        order = torch.cat([top, bot, mid]).to(torch.int32).contiguous()
+        sizes = torch.cat([top_sz, bot_sz, mid_sz])
+        tile_ptr = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=dev)
+        tile_ptr[1:] = torch.cumsum(sizes, 0)
+        assert order.numel() == g.n_dst and int(tile_ptr[-1]) == g.n_dst
+        self.n_boundary = int(top_sz.numel() + bot_sz.numel())
+        self.n_interior = int(mid_sz.numel())
+        self.plan = g.tile_plan_from(order, tile_ptr.to(torch.int32), tw + 2,
+                                     ("band", th, tw, strip_width))
+        self.side = torch.cuda.Stream(device=dev)
+
+    def __call__(self, x_local: torch.Tensor, bias=None, relu: bool = False, out=None) -> torch.Tensor:
+        from ._lib import lib
+        g = self.local.graph
+        cur = torch.cuda.current_stream(x_local.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            self.hx.exchange(x_local)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        if out is None:
+            shape = tuple(x_local.shape[:-2]) + (g.n_dst, x_local.shape[-1])
+            out = torch.empty(shape, dtype=x_local.dtype, device=x_local.device)
+        kw = dict(bias=bias, relu=relu, kernel="tiled", out=out, plan=self.plan)
+        if self.n_interior:
+            old = lib().gwen_set_sm_reserve(self.sm_reserve)
+            try:
+                ops.aggregate(g, x_local, tile_range=(self.n_boundary, self.n_interior), **kw)
+            finally:
+                lib().gwen_set_sm_reserve(old)
+        cur.wait_event(done)
+        ops.aggregate(g, x_local, tile_range=(0, self.n_boundary), **kw)
+        return out

@@ -56,6 +56,11 @@ enum {
 enum { GWEN_EPI_NONE = 0, GWEN_EPI_RELU = 1 };
 
 int gwen_version(void);
+/* The persistent kernels (tiled aggregation, tensor-core GEMM) launch one CTA per SM.  A caller
+ * that overlaps them with small kernels on another stream (halo packs, NCCL send/recv) reserves
+ * n SMs for those: subsequent persistent launches use (SM count - n) CTAs.  Returns the previous
+ * value; process-wide. */
+int gwen_set_sm_reserve(int n);
 /* Last error message of the calling thread ("" if none).  Pointer stays valid until the next
  * failing call on this thread. */
 const char* gwen_last_error(void);
@@ -165,10 +170,13 @@ int gwen_grid_tiles(int64_t height, int64_t width, int32_t th, int32_t tw, int32
 /* slab_elems: feature columns staged per work item: 8, 16 or 32 sixteen-byte chunks
  * (0 = widest that fits); two stages of max_tile_runs * run_len * slab bytes must fit in the
  * 227 KB of shared memory, else GWEN_E_NOSUPPORT (use gwen_aggregate_fwd). */
+/* tile_begin / tile_count: process only tiles [tile_begin, tile_begin + tile_count) of the plan
+ * (0, 0 = all) -- lets a partitioned run launch interior tiles while the halo is in flight. */
 int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const void* x, void* out,
                              int64_t batch, int64_t n_src, int64_t feat, int64_t ldx,
                              int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
-                             const float* bias, int epilogue, int32_t slab_elems, void* stream);
+                             const float* bias, int epilogue, int32_t slab_elems,
+                             int32_t tile_begin, int32_t tile_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
