@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[2][256];  // the tile's bias slice, double-buffered
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = uint32_t(g.bn) * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -316,6 +317,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++seq) {
       const int m0 = int(tile / n_tiles) * BM, n0 = int(tile % n_tiles) * g.bn;
       const uint32_t acc = seq & 1u;
+      // stage this tile's bias slice once (128 epilogue threads, <= 256 values) instead of
+      // re-reading it from global memory per row; buffer `acc` was last read two tiles ago and
+      // every epilogue warp has passed the named barrier of the tile in between.
+      {
+        const int et = int(threadIdx.x) - 64;
+        for (int i = et; i < g.bn; i += 128) bias_s[acc][i] = g.bias ? __ldg(g.bias + n0 + i) : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
       tc_fence_after();
       const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
@@ -337,8 +346,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           float f[8];
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            f[t] = __uint_as_float(j < 4 ? r0[j * 8 + t] : r1[(j - 4) * 8 + t]);
-            if (g.bias) f[t] += __ldg(g.bias + n0 + c + j * 8 + t);
+            f[t] = __uint_as_float(j < 4 ? r0[j * 8 + t] : r1[(j - 4) * 8 + t]) +
+                   bias_s[acc][c + j * 8 + t];
             if (g.relu) f[t] = fmaxf(f[t], 0.0f);
           }
           uint4 o;
