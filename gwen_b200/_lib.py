@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "linear.cu", "linear_tc.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu"]
 HEADERS = ["common.cuh", "tma.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
@@ -85,6 +85,8 @@ PROTOTYPES = {
     "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _i64, _i64, _i64,
                                         _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _i32, _i32,
                                         _p]),
+    "gwen_grid_stencil_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                     _i64, _i64, _int, _p, _int, _i32, _i32, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,

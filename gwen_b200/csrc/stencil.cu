@@ -1,0 +1,336 @@
+// K1s: aggregation fast path for mesh graphs (the COSMO-shaped grids of BASELINE configs 2-5).
+//
+// When the graph is exactly the 8-neighbour H x W mesh with GCN normalisation (K0 detects this),
+//   out[r, c] = dis[r, c] * sum_{dr, dc in {-1,0,1}} dis[r+dr, c+dc] * x[r+dr, c+dc]     (valid nodes)
+// is a separable 3 x 3 box filter of y = dis * x.  The CSR kernels read 9 staged source rows per
+// destination through the 128 B/clk shared-memory pipe (the measured bound of k_agg_tiled, LSU data
+// pipe 72 %); here a sub-warp slides along a destination row holding the last three COLUMN sums
+//   s[t] = (dis*x)[r-1, t] + (dis*x)[r, t] + (dis*x)[r+1, t]
+// in registers, so each destination costs 3 shared-memory row reads, and the kernel goes back to
+// being HBM-bound.
+//
+// Data movement: work item = (tile of TH x TW destinations, batch b, feature slab).  One lane
+// issues ONE cp.async.bulk.tensor.4d per item: the box {slab, TW+2, TH+2, 1} of x viewed as
+// [B][Hs][W][F], plus one 2-D box of the (padded) dis array.  Coordinates start one row/column
+// outside the tile; TMA zero-fills everything outside the mesh, which IS the truncated stencil of
+// border nodes (their missing neighbours contribute 0).  Warp-specialised, NS-stage full/empty
+// mbarrier ring as in k_agg_tiled.
+//
+// Summation order differs from the CSR order (column sums first), so results are not bitwise
+// equal to gwen_aggregate_fwd: they agree to fp32 rounding (tests: <= 1e-6 normalised) and are
+// deterministic and independent of tiling / partitioning (each destination's order is fixed by
+// geometry alone).
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace gwen {
+namespace {
+
+constexpr int TH = 8;     // destination rows per tile
+constexpr int SEG = 8;    // destination columns a sub-warp walks per unit
+
+template <typename T>
+struct V16;
+template <>
+struct V16<float> {
+  static constexpr int N = 4;
+  __device__ static void unpack(const uint4& r, float* f) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+    f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+  __device__ static uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+};
+template <>
+struct V16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void unpack(const uint4& r, float* f) {
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(u[i] << 16);
+      f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+  __device__ static uint4 pack(const float* f) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      u[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+  }
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, int c0, int c1,
+                                            int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+// Plain bulk copy global -> shared (contiguous, multiple of 16 bytes), completing on `bar`.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+struct StencilArgs {
+  void* out;
+  const float* bias;
+  int64_t batch, feat, ldo, o_bstride;
+  int hd, w, row_off;        // destination rows, mesh width, source row of destination row 0
+  int tw, tiles_x, num_tiles, slabs, slab_elems, relu, num_stages;
+  uint32_t x_bytes, dis_pitch, stage_bytes;  // bytes of the x box, dis box row pitch, one stage
+  const float* disb;       // zero-bordered dis, [hs + 2][disb_pitch]
+  int64_t disb_pitch;
+};
+
+// LPR lanes cover one slab (LPR * 16 bytes); 32/LPR sub-warps per warp, each walks one unit
+// (destination row r of the tile, columns [seg*SEG, seg*SEG + SEG)).
+template <typename T, int LPR>
+__global__ void __launch_bounds__(544, 1)
+    k_grid_stencil(const __grid_constant__ CUtensorMap xmap, StencilArgs a) {
+  constexpr int VN = V16<T>::N;
+  constexpr int RPW = 32 / LPR;
+  constexpr int MAXS = 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAXS], empty_bar[MAXS];
+  const int ns = a.num_stages;
+  const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ncw = nwarps - 1;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&xmap);
+    for (int i = 0; i < ns; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), ncw);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int per_tile = static_cast<int>(a.batch) * a.slabs;
+  const int my_tiles = a.num_tiles > int(blockIdx.x)
+                           ? (a.num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+  const int64_t n_items = int64_t(my_tiles) * per_tile;
+  const uint32_t slab_bytes = a.slab_elems * sizeof(T);
+  const uint32_t srow_bytes = uint32_t(a.tw + 2) * slab_bytes;  // one staged mesh row
+
+  if (warp == ncw) {
+    if (lane == 0) {  // ===== producer =====
+      int st = 0;
+      uint32_t round = 0;
+      for (int64_t it = 0; it < n_items; ++it) {
+        const int t = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+        const int rem = int(it % per_tile);
+        const int b = rem / a.slabs, slab = rem % a.slabs;
+        const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
+        if (round > 0) mbar_wait(smem_u32(&empty_bar[st]), (round - 1) & 1u);
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        const uint32_t dst = stage0 + uint32_t(st) * a.stage_bytes;
+        mbar_expect_tx(bar, a.x_bytes + uint32_t(TH + 2) * a.dis_pitch);
+        tma_load_4d(dst, &xmap, slab * a.slab_elems, c0 - 1, r0 + a.row_off - 1, b, bar);
+        // dis box: TH+2 rows of the zero-bordered dis array (element [r+1][c+1] = dis[r][c]),
+        // so mesh node (r0+row_off-1+i, c0-1+t) sits at disb[(r0+row_off+i) * pitch + c0 + t].
+        const float* dsrc = a.disb + int64_t(r0 + a.row_off) * a.disb_pitch + c0;
+        for (int i = 0; i < TH + 2; ++i)
+          bulk_g2s(dst + a.x_bytes + uint32_t(i) * a.dis_pitch, dsrc + int64_t(i) * a.disb_pitch,
+                   a.dis_pitch, bar);
+        if (++st == ns) { st = 0; ++round; }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int sub = lane / LPR, l = lane % LPR;
+  const int nseg = a.tw / SEG;
+  const int units = TH * nseg;
+  int st = 0;
+  uint32_t round = 0;
+  for (int64_t it = 0; it < n_items; ++it) {
+    const int t = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+    const int rem = int(it % per_tile);
+    const int b = rem / a.slabs, slab = rem % a.slabs;
+    const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
+    const int rows_valid = min(TH, a.hd - r0), cols_valid = min(a.tw, a.w - c0);
+    const int64_t col = int64_t(slab) * a.slab_elems + int64_t(l) * VN;
+    const bool on = col < a.feat;
+    const uint32_t xs = stage0 + uint32_t(st) * a.stage_bytes;
+    const uint32_t ds = xs + a.x_bytes;
+    float bv[VN];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) bv[k] = (a.bias && on) ? __ldg(a.bias + col + k) : 0.0f;
+    T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
+    mbar_wait(smem_u32(&full_bar[st]), round & 1u);
+    for (int u = warp * RPW + sub; u < units; u += ncw * RPW) {
+      const int r = u / nseg, cb = (u % nseg) * SEG;
+      if (r >= rows_valid || cb >= cols_valid) continue;
+      // staged rows r, r+1, r+2 hold mesh rows (r0+r-1 .. r0+r+1); staged column t = mesh c0-1+t
+      const uint32_t xrow = xs + uint32_t(r) * srow_bytes + uint32_t(cb) * slab_bytes + uint32_t(l) * 16u;
+      const uint32_t drow = ds + uint32_t(r) * a.dis_pitch + uint32_t(cb) * 4u;
+      float s0[VN], s1[VN], s2[VN];  // column sums of staged columns t-2, t-1, t
+      float dmid_prev = 0.0f;        // dis of the destination under the window centre
+#pragma unroll
+      for (int tt = 0; tt < SEG + 2; ++tt) {
+        const uint4 v0 = lds128(xrow + uint32_t(tt) * slab_bytes);
+        const uint4 v1 = lds128(xrow + srow_bytes + uint32_t(tt) * slab_bytes);
+        const uint4 v2 = lds128(xrow + 2 * srow_bytes + uint32_t(tt) * slab_bytes);
+        const float d0 = lds32(drow + uint32_t(tt) * 4u);
+        const float d1 = lds32(drow + a.dis_pitch + uint32_t(tt) * 4u);
+        const float d2 = lds32(drow + 2 * a.dis_pitch + uint32_t(tt) * 4u);
+        float f0[VN], f1[VN], f2[VN];
+        V16<T>::unpack(v0, f0);
+        V16<T>::unpack(v1, f1);
+        V16<T>::unpack(v2, f2);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+          s0[k] = s1[k];
+          s1[k] = s2[k];
+          s2[k] = fmaf(d2, f2[k], fmaf(d1, f1[k], d0 * f0[k]));
+        }
+        if (tt >= 2) {  // destination column j = cb + tt - 2 (window = staged columns tt-2 .. tt)
+          const int j = cb + tt - 2;
+          if (j < cols_valid && on) {
+            float o[VN];
+#pragma unroll
+            for (int k = 0; k < VN; ++k) {
+              o[k] = dmid_prev * ((s0[k] + s1[k]) + s2[k]) + bv[k];
+              if (a.relu) o[k] = fmaxf(o[k], 0.0f);
+            }
+            stg128(ob + (int64_t(r0 + r) * a.w + (c0 + j)) * a.ldo, V16<T>::pack(o));
+          }
+        }
+        dmid_prev = d1;  // dis of mesh node (r0+r, c0-1+tt): the centre of the NEXT window
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
+    if (++st == ns) { st = 0; ++round; }
+  }
+}
+
+inline int env_int2(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+template <typename T, int LPR>
+int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, cudaStream_t st) {
+  auto kern = k_grid_stencil<T, LPR>;
+  GWEN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  const int grid = std::min(a.num_tiles, std::max(1, sm_count() - sm_reserve()));
+  // consumer sub-warps = TH * tw / SEG units when possible: 16 consumer warps + 1 producer warp
+  kern<<<grid, 544, smem, st>>>(xmap, a);
+  GWEN_LAUNCH_CHECK("k_grid_stencil");
+  return GWEN_OK;
+}
+
+}  // namespace
+}  // namespace gwen
+
+using namespace gwen;
+
+extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded,
+                                     int64_t dis_pitch, int64_t batch, int64_t hs, int64_t hd,
+                                     int64_t w, int64_t row_off, int64_t feat, int64_t ldx,
+                                     int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
+                                     const float* bias, int epilogue, int32_t slab_elems,
+                                     int32_t tile_w, void* stream) {
+  GWEN_CHECK_ARG(batch >= 0 && hs >= 0 && hd >= 0 && w >= 0 && feat >= 0, "negative size");
+  if (batch == 0 || hd == 0 || w == 0 || feat == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(x && out && dis_padded, "null pointer");
+  GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
+  GWEN_CHECK_ARG(row_off >= 0 && row_off + hd <= hs + 1, "row_off outside the source rows");
+  GWEN_CHECK_ARG(dis_pitch % 4 == 0 && aligned16(dis_padded),
+                 "bordered dis needs a pitch that is a multiple of 4 floats and a 16-byte base");
+  GWEN_CHECK_ARG(hs * w < INT32_MAX && batch < 65536, "mesh too large");
+  const int esz = dtype == GWEN_F32 ? 4 : 2;
+  const int vn = 16 / esz;
+  if (feat % vn || ldx % vn || ldo % vn || x_bstride % vn || o_bstride % vn || !aligned16(x) ||
+      !aligned16(out))
+    return set_err(GWEN_E_ALIGN, "grid stencil needs 16-byte aligned rows (feat %% %d == 0)", vn);
+  int tw = tile_w > 0 ? tile_w : 32;
+  GWEN_CHECK_ARG(tw % SEG == 0 && tw >= SEG && tw <= 128, "tile_w must be a multiple of %d", SEG);
+  int lpr = slab_elems > 0 ? static_cast<int>(slab_elems / vn) : 16;
+  if (lpr != 8 && lpr != 16 && lpr != 32)
+    return set_err(GWEN_E_BADARG, "slab_elems must be %d, %d or %d", 8 * vn, 16 * vn, 32 * vn);
+  while (lpr > 8 && lpr * vn / 2 >= feat) lpr /= 2;
+  const uint32_t dis_box_w = static_cast<uint32_t>((tw + 2 + 3) / 4 * 4);
+  auto stage_for = [&](int lpr_) {
+    size_t xb = size_t(TH + 2) * (tw + 2) * lpr_ * 16;
+    return align_up(xb + size_t(TH + 2) * dis_box_w * 4, 128);
+  };
+  const size_t smem_cap = 226 * 1024;
+  while (lpr > 8 && 2 * stage_for(lpr) + 256 > smem_cap) lpr /= 2;
+  if (2 * stage_for(lpr) + 256 > smem_cap)
+    return set_err(GWEN_E_NOSUPPORT, "stencil tile does not fit in shared memory");
+  static const int stage_hint = env_int2("GWEN_STENCIL_STAGES", 3, 2, 8);
+  int ns = 2;
+  while (ns < stage_hint && (ns + 1) * stage_for(lpr) + 256 <= smem_cap) ++ns;
+  const int slab = lpr * vn;
+  // x viewed as [B][Hs][W][F]; box {slab, tw+2, TH+2, 1}, no swizzle, zero fill outside the mesh
+  auto enc = tensor_map_encoder();
+  if (!enc) return set_err(GWEN_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUtensorMap xmap;
+  {
+    cuuint64_t dims[4] = {cuuint64_t(feat), cuuint64_t(w), cuuint64_t(hs), cuuint64_t(batch)};
+    cuuint64_t strides[3] = {cuuint64_t(ldx) * esz, cuuint64_t(w) * ldx * esz,
+                             cuuint64_t(batch > 1 ? x_bstride : hs * w * ldx) * esz};
+    cuuint32_t box[4] = {cuuint32_t(slab), cuuint32_t(tw + 2), cuuint32_t(TH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&xmap, dtype == GWEN_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     4, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(GWEN_E_CUDA, "x tensor map encode failed (%d)", int(r));
+  }
+  const int tiles_x = static_cast<int>(ceil_div(w, tw)), tiles_y = static_cast<int>(ceil_div(hd, TH));
+  StencilArgs a{out, bias, batch, feat, ldo, o_bstride, static_cast<int>(hd), static_cast<int>(w),
+                static_cast<int>(row_off), tw, tiles_x, tiles_x * tiles_y,
+                static_cast<int>(ceil_div(feat, slab)), slab, (epilogue & GWEN_EPI_RELU) ? 1 : 0, ns,
+                static_cast<uint32_t>(size_t(TH + 2) * (tw + 2) * lpr * 16), dis_box_w * 4,
+                static_cast<uint32_t>(stage_for(lpr)), dis_padded, dis_pitch};
+  if (dis_pitch < int64_t(tiles_x - 1) * tw + dis_box_w)
+    return set_err(GWEN_E_BADARG, "bordered dis pitch %lld < %lld needed for tile width %d",
+                   (long long)dis_pitch, (long long)(int64_t(tiles_x - 1) * tw + dis_box_w), tw);
+  const size_t smem = ns * stage_for(lpr) + 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GWEN_F32) {
+    if (lpr == 32) return launch_stencil<float, 32>(xmap, a, smem, st);
+    if (lpr == 16) return launch_stencil<float, 16>(xmap, a, smem, st);
+    return launch_stencil<float, 8>(xmap, a, smem, st);
+  }
+  if (lpr == 32) return launch_stencil<__nv_bfloat16, 32>(xmap, a, smem, st);
+  if (lpr == 16) return launch_stencil<__nv_bfloat16, 16>(xmap, a, smem, st);
+  return launch_stencil<__nv_bfloat16, 8>(xmap, a, smem, st);
+}

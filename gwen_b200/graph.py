@@ -106,6 +106,16 @@ class TilePlan:
         return self.total_runs * self.run_len / max(1, self.n_dst)
 
 
+def bordered_dis(dis2d: torch.Tensor) -> torch.Tensor:
+    """[H, W] -> zero-bordered fp32 [round_up(H, 8) + 4, pitch] as gwen_grid_stencil_fwd expects
+    (rows padded so the last 8-row tile can fetch its full box)."""
+    h, w = dis2d.shape
+    pitch = (w + 128 + 8 + 3) // 4 * 4
+    d = torch.zeros(((h + 7) // 8 * 8 + 4, pitch), dtype=torch.float32, device=dis2d.device)
+    d[1:h + 1, 1:w + 1] = dis2d
+    return d
+
+
 class GraphCSR:
     """Destination-sorted CSR of ``edge_index'`` (after self-loop normalisation) with GCN weights.
 
@@ -126,6 +136,23 @@ class GraphCSR:
     @property
     def device(self):
         return self.rowptr.device
+
+    # -- mesh fast path ------------------------------------------------------------------------
+    @property
+    def is_plain_mesh(self) -> bool:
+        """True when this is exactly the H x W 8-neighbour mesh with default GCN normalisation
+        (self loops added, weight 1) over all of its nodes: the stencil kernel applies."""
+        return (self.grid_shape is not None and self.dis is not None and self.n_src == self.n_dst
+                and self.flags == _lib.GRAPH_ADD_SELF_LOOPS
+                and self.grid_shape[0] * self.grid_shape[1] == self.n_dst)
+
+    def dis_padded(self) -> torch.Tensor:
+        """dis with a one-element zero border, [H + 2, pitch] (element [r+1][c+1] = dis[r][c]),
+        pitch sized for any stencil tile width up to 128; cached."""
+        if getattr(self, "_dis_padded", None) is None:
+            h, w = self.grid_shape
+            self._dis_padded = bordered_dis(self.dis.view(h, w))
+        return self._dis_padded
 
     # -- backward graph ----------------------------------------------------------------------
     def transposed(self) -> "GraphCSR":

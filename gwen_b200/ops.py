@@ -15,13 +15,16 @@ from . import _lib
 from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
-__all__ = ["aggregate", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad",
+__all__ = ["aggregate", "mesh_stencil", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad",
            "rows_gather", "rows_scatter_", "dtype_code"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
 
-# Which K1 kernel `aggregate` uses: "auto" (tiled when the graph is a grid and rows are
-# 16-byte multiples), "rows", "tiled".  bench.py / tests override it explicitly.
+# Which K1 kernel `aggregate` uses:
+#   "rows"    generic CSR kernel (any graph), fp32 bit-exact vs the CPU scatter_add_ order
+#   "tiled"   TMA-staged CSR kernel for mesh graphs, bitwise equal to "rows"
+#   "stencil" separable mesh fast path (plain H x W mesh only), equal to fp32 rounding
+#   "auto"    stencil on a plain mesh with 16-byte rows, else rows
 DEFAULT_AGG_KERNEL = "auto"
 
 
@@ -63,7 +66,7 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
     kernel = kernel or DEFAULT_AGG_KERNEL
     esz = x3.element_size()
     if kernel == "auto":
-        kernel = "tiled" if (graph.grid_shape is not None and (f * esz) % 16 == 0 and f * esz >= 128) else "rows"
+        kernel = "stencil" if (graph.is_plain_mesh and (f * esz) % 16 == 0) else "rows"
     bias32 = _bias32(bias)
     with torch.cuda.device(x3.device):
         if out is None:
@@ -78,6 +81,15 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
                                                  tile_range[0] if tile_range else 0,
                                                  tile_range[1] if tile_range else 0,
                                                  _stream()), "gwen_aggregate_tiled_fwd")
+        elif kernel == "stencil":
+            if not graph.is_plain_mesh:
+                raise RuntimeError("the stencil kernel needs a plain H x W mesh graph")
+            h, w = graph.grid_shape
+            dpad = graph.dis_padded()
+            check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(out), _ptr(dpad), dpad.shape[1], b, h, h, w,
+                                              0, f, f, n_src * f, f, graph.n_dst * f, code,
+                                              _ptr(bias32), epi, slab, tile[0] if tile else 0,
+                                              _stream()), "gwen_grid_stencil_fwd")
         elif kernel == "rows":
             check(lib().gwen_aggregate_fwd(_ptr(graph.rowptr), _ptr(graph.src), _ptr(graph.w),
                                            _ptr(graph.order), _ptr(x3), _ptr(out), b, graph.n_dst,
@@ -86,6 +98,30 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
         else:
             raise ValueError("unknown aggregate kernel %r" % kernel)
     return out.reshape(tuple(lead) + (graph.n_dst, f))
+
+
+def mesh_stencil(x: torch.Tensor, dis_bordered: torch.Tensor, hs: int, hd: int, w: int, row_off: int,
+                 bias: Optional[torch.Tensor] = None, relu: bool = False,
+                 out: Optional[torch.Tensor] = None, slab: int = 0, tile_w: int = 0) -> torch.Tensor:
+    """Mesh fast path on explicit geometry: x [B, hs*w, F] -> out [B, hd*w, F], destination row r
+    reads source rows r + row_off - 1 .. r + row_off + 1 (see gwen_grid_stencil_fwd)."""
+    _require_cuda(x, "x")
+    x3, lead = _as_3d(x)
+    b, n_src, f = x3.shape
+    if n_src != hs * w:
+        raise ValueError("x has %d rows, expected hs * w = %d" % (n_src, hs * w))
+    code = dtype_code(x3.dtype)
+    bias32 = _bias32(bias)
+    with torch.cuda.device(x3.device):
+        if out is None:
+            out = torch.empty((b, hd * w, f), dtype=x3.dtype, device=x3.device)
+        o3 = out if out.dim() == 3 else out.unsqueeze(0)
+        assert o3.is_contiguous() or o3.stride(-1) == 1
+        check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(o3), _ptr(dis_bordered), dis_bordered.shape[1],
+                                          b, hs, hd, w, row_off, f, f, n_src * f, f, o3.stride(0) if b > 1 else hd * w * f,
+                                          code, _ptr(bias32), _lib.EPI_RELU if relu else 0, slab, tile_w,
+                                          _stream()), "gwen_grid_stencil_fwd")
+    return out
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,

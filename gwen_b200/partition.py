@@ -21,9 +21,9 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .graph import GraphCSR
+from .graph import GraphCSR, bordered_dis
 
-__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator"]
+__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator", "MeshBand"]
 
 
 def band_ranges(height: int, width: int, world_size: int) -> List[range]:
@@ -196,4 +196,107 @@ class BandAggregator:
                 lib().gwen_set_sm_reserve(old)
         cur.wait_event(done)
         ops.aggregate(g, x_local, tile_range=(0, self.n_boundary), **kw)
+        return out
+
+
+class MeshBand:
+    """A rank's row band of a plain H x W mesh for the stencil fast path.
+
+    Local feature layout: ``[B, (rows + 2) * W, F]`` = ``[top halo row | owned rows | bottom halo
+    row]`` in mesh order, so every halo is one contiguous row and (for B = 1) is sent and received
+    in place, without pack kernels.  Halo rows outside the mesh stay zero and carry ``dis = 0``.
+    ``aggregate`` overlaps the exchange with the interior rows: exchange on a side stream, interior
+    destination rows [1, rows-1) on the caller's stream (``sm_reserve`` SMs left free for the NCCL
+    kernels), then the first and last owned rows once the halos have arrived.
+    Results are bitwise equal to the single-GPU stencil kernel on the whole mesh.
+    """
+
+    def __init__(self, height: int, width: int, dis_global: torch.Tensor, group=None, sm_reserve: int = 8,
+                 rank: Optional[int] = None, world: Optional[int] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.H, self.W, self.sm_reserve = height, width, sm_reserve
+        ranges = band_ranges(height, width, self.world)
+        own = ranges[self.rank]
+        self.r0, self.rows = own.start // width, len(own) // width
+        dev = dis_global.device
+        d2 = dis_global.view(height, width)
+        local = torch.zeros((self.rows + 2, width), dtype=torch.float32, device=dev)
+        lo, hi = max(self.r0 - 1, 0), min(self.r0 + self.rows + 1, height)
+        local[lo - (self.r0 - 1):hi - (self.r0 - 1)] = d2[lo:hi]
+        self.dis = bordered_dis(local)
+        self.up = self.rank - 1 if self.rank > 0 else None
+        self.down = self.rank + 1 if self.rank < self.world - 1 else None
+        self.side = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    @property
+    def n_own(self) -> int:
+        return self.rows * self.W
+
+    @property
+    def n_local(self) -> int:
+        return (self.rows + 2) * self.W
+
+    def alloc(self, batch: int, feat: int, dtype, device) -> torch.Tensor:
+        """Zero-initialised local feature buffer (halo rows outside the mesh must stay zero)."""
+        return torch.zeros((batch, self.n_local, feat), dtype=dtype, device=device)
+
+    def owned(self, x_local: torch.Tensor) -> torch.Tensor:
+        return x_local[..., self.W:self.W + self.n_own, :]
+
+    def exchange(self, x_local: torch.Tensor) -> None:
+        """Fill the halo rows from the neighbouring ranks (x_local [B, n_local, F] contiguous)."""
+        w, rows = self.W, self.rows
+        x3 = x_local if x_local.dim() == 3 else x_local.unsqueeze(0)
+        first, last = slice(w, 2 * w), slice(rows * w, (rows + 1) * w)
+        top, bot = slice(0, w), slice((rows + 1) * w, (rows + 2) * w)
+        p2p, post = [], []
+        for peer, snd, rcv in ((self.up, first, top), (self.down, last, bot)):
+            if peer is None:
+                continue
+            if x3.shape[0] == 1:
+                sbuf, rbuf = x3[0, snd], x3[0, rcv]       # contiguous rows: in place
+            else:
+                sbuf = x3[:, snd].contiguous()
+                rbuf = torch.empty_like(sbuf)
+                post.append((rcv, rbuf))
+            p2p.append(dist.P2POp(dist.isend, sbuf, peer, self.group))
+            p2p.append(dist.P2POp(dist.irecv, rbuf, peer, self.group))
+        if p2p:
+            for req in dist.batch_isend_irecv(p2p):
+                req.wait()
+        for rcv, rbuf in post:
+            x3[:, rcv] = rbuf
+
+    def aggregate(self, x_local: torch.Tensor, bias=None, relu: bool = False, out=None,
+                  overlap: bool = True) -> torch.Tensor:
+        from ._lib import lib
+        w, rows = self.W, self.rows
+        x3 = x_local if x_local.dim() == 3 else x_local.unsqueeze(0)
+        b, _, f = x3.shape
+        if out is None:
+            out = torch.empty((b, self.n_own, f), dtype=x3.dtype, device=x3.device)
+        o3 = out if out.dim() == 3 else out.unsqueeze(0)
+        kw = dict(bias=bias, relu=relu)
+        if not overlap or rows < 3:
+            self.exchange(x3)
+            ops.mesh_stencil(x3, self.dis, rows + 2, rows, w, 1, out=o3, **kw)
+            return out
+        cur = torch.cuda.current_stream(x3.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.side.wait_event(ready)
+        with torch.cuda.stream(self.side):
+            self.exchange(x3)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        old = lib().gwen_set_sm_reserve(self.sm_reserve)
+        try:   # interior destination rows 1 .. rows-2 read owned rows only
+            ops.mesh_stencil(x3, self.dis, rows + 2, rows - 2, w, 2, out=o3[:, w:(rows - 1) * w], **kw)
+        finally:
+            lib().gwen_set_sm_reserve(old)
+        cur.wait_event(done)
+        ops.mesh_stencil(x3, self.dis, rows + 2, 1, w, 1, out=o3[:, :w], **kw)
+        ops.mesh_stencil(x3, self.dis, rows + 2, 1, w, rows, out=o3[:, (rows - 1) * w:], **kw)
         return out

@@ -179,6 +179,27 @@ int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const void* x, voi
                              int32_t tile_begin, int32_t tile_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1s  mesh fast path of the aggregation (same reference steps as K1: rows 7-11).
+ * For the exact 8-neighbour H x W mesh with GCN normalisation (what gwen_grid_edges builds and
+ * K0 normalises; the host layer checks this before choosing it):
+ *   out[b, r, c, :] = epi( dis[r', c] * sum_{dr, dc in {-1,0,1}} dis[r'+dr, c+dc] * x[b, r'+dr, c+dc, :] + bias )
+ * with r' = r + row_off and nodes outside [0, hs) x [0, w) contributing 0.  Evaluated as a
+ * separable box filter (column sums in registers), sources staged by one 4-D TMA box per tile.
+ *   x   : [B, hs, w, F] (node pitch ldx, batch stride x_bstride)      out : [B, hd, w, F]
+ *   dis_padded : fp32 [>= round_up(hd, 8) + row_off + 2, dis_pitch] with a one-element ZERO
+ *                border (and zero padding): element [r+1][c+1] = dis[r][c]; dis_pitch % 4 == 0 and >= (ceil(w / tile_w) - 1) * tile_w +
+ *                round_up(tile_w + 2, 4); 16-byte aligned (rows are fetched with bulk copies)
+ *   row_off    : source row of destination row 0 (0 for a whole mesh; 1 for a row band whose x
+ *                carries one halo row above and below: hs = hd + 2)
+ * Agrees with gwen_aggregate_fwd to fp32 rounding (different summation order), deterministic,
+ * independent of tiling and partitioning. */
+int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded, int64_t dis_pitch,
+                          int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
+                          int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo,
+                          int64_t o_bstride, int dtype, const float* bias, int epilogue,
+                          int32_t slab_elems, int32_t tile_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
  * SURVEY.md table 2.3 row 6) and, through the epilogue, the bias add and ReLU when the
  * projection runs after the aggregation:

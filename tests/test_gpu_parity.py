@@ -463,3 +463,98 @@ def test_band_plan_matches_plain_plan(dev):
     ref = ops.aggregate(g, x, b, kernel="rows")
     assert torch.equal(band(x, b), ref)
     assert torch.equal(ops.aggregate(g, x, b, kernel="tiled", plan=band.plan), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1s mesh stencil fast path
+# ---------------------------------------------------------------------------------------------
+STENCIL_TOL = 1e-6   # fp32: same terms, different (separable) summation order
+
+
+@pytest.mark.parametrize("hw", [(2, 2), (3, 4), (8, 32), (9, 33), (17, 23), (40, 70), (5, 130), (64, 7)])
+@pytest.mark.parametrize("feat,slab,tw", [(64, 0, 0), (256, 0, 0), (256, 128, 16), (36, 32, 8), (520, 64, 64)])
+def test_stencil_fp32_vs_oracle(dev, hw, feat, slab, tw):
+    h, w = hw
+    ei = orc.grid(h, w)
+    g = gw.build_graph(ei.to(dev), h * w)
+    assert g.is_plain_mesh
+    x = wts.features((h * w, feat), 11)
+    b = wts.small_bias(feat, 12)
+    ref = oracle_aggregate(x, ei, h * w, b, True)
+    out = ops.aggregate(g, x.to(dev), b.to(dev), relu=True, kernel="stencil", slab=slab,
+                        tile=(tw,) if tw else None)
+    assert nmax(out, ref) <= STENCIL_TOL
+    dense = torch.relu(orc.dense_norm_adj(ei, h * w) @ x.double() + b.double()) if h * w <= 1000 else None
+    if dense is not None:
+        assert nmax(out, dense) <= STENCIL_TOL
+    # the graph without its explicit self loops normalises to the same operator
+    g2 = gw.build_graph(ei[:, ei[0] != ei[1]].to(dev), h * w)
+    assert g2.is_plain_mesh
+    assert torch.equal(ops.aggregate(g2, x.to(dev), b.to(dev), relu=True, kernel="stencil", slab=slab,
+                                     tile=(tw,) if tw else None), out)
+
+
+def test_stencil_batched_bf16_deterministic_and_auto(dev):
+    h, w, f = 30, 45, 128
+    ei = orc.grid(h, w)
+    g = gw.build_graph(ei.to(dev), h * w)
+    x = wts.features((3, h * w, f), 9)
+    out = ops.aggregate(g, x.to(dev), kernel="stencil")
+    for i in range(3):
+        assert nmax(out[i], oracle_aggregate(x[i], ei, h * w)) <= STENCIL_TOL
+    assert torch.equal(out, ops.aggregate(g, x.to(dev), kernel="stencil"))          # run-to-run
+    assert torch.equal(out, ops.aggregate(g, x.to(dev)))                             # auto -> stencil
+    assert torch.equal(out, ops.aggregate(g, x.to(dev), kernel="stencil", tile=(16,), slab=32))  # tiling-independent
+    assert nmax(out, ops.aggregate(g, x.to(dev), kernel="tiled")) <= STENCIL_TOL
+    xb = x.to(torch.bfloat16)
+    outb = ops.aggregate(g, xb.to(dev), kernel="stencil")
+    ref = oracle_aggregate(xb.float(), ei, h * w)
+    assert torch.all((outb.float().cpu() - ref).abs() <= ref.abs() * 2.0 ** -7 + 1e-6)
+    # not a plain mesh -> refused / auto falls back to the CSR kernel
+    gi = gw.build_graph(ei.to(dev), h * w, improved=True)
+    assert not gi.is_plain_mesh
+    with pytest.raises(RuntimeError):
+        ops.aggregate(gi, x.to(dev), kernel="stencil")
+    gr = gw.build_graph(GRAPHS["random"]()[0].to(dev), 300)
+    assert not gr.is_plain_mesh
+
+
+def test_stencil_large_mesh(dev):
+    """BASELINE config 2 size: stencil vs the bit-exact tiled kernel, and a band vs the oracle."""
+    h, w, f = 582, 390, 256
+    g = gw.get_graph(gw.grid(h, w, dev), h * w)
+    x = torch.randn(h * w, f, device=dev)
+    b = torch.randn(f, device=dev)
+    a = ops.aggregate(g, x, b, kernel="stencil")
+    assert nmax(a, ops.aggregate(g, x, b, kernel="tiled")) <= STENCIL_TOL
+    sub = x[98 * w:106 * w].cpu()
+    ref = oracle_aggregate(sub, orc.grid(8, w), 8 * w, b.cpu())
+    assert nmax(a[100 * w:104 * w], ref[2 * w:6 * w]) <= STENCIL_TOL
+    gw.clear_graph_cache()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_mesh_band_stencil_equals_single_gpu(dev, world):
+    """Row-band partition of the stencil path, all ranks emulated on one GPU: every band's output
+    (whole-band launch and the interior / first-row / last-row split) is BITWISE equal to the
+    single-GPU stencil on the whole mesh."""
+    from gwen_b200 import partition
+    h, w, f = 41, 50, 64
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    x = torch.randn(2, h * w, f, device=dev)
+    b = torch.randn(f, device=dev)
+    full = ops.aggregate(g, x, b, relu=True, kernel="stencil")
+    for rank in range(world):
+        band = partition.MeshBand(h, w, g.dis, rank=rank, world=world)
+        xl = band.alloc(2, f, torch.float32, dev)
+        lo, hi = max(band.r0 - 1, 0), min(band.r0 + band.rows + 1, h)
+        xl[:, (lo - (band.r0 - 1)) * w:(hi - (band.r0 - 1)) * w] = x[:, lo * w:hi * w]   # halos as exchanged
+        want = full[:, band.r0 * w:(band.r0 + band.rows) * w]
+        rows = band.rows
+        out = ops.mesh_stencil(xl, band.dis, rows + 2, rows, w, 1, bias=b, relu=True)
+        assert torch.equal(out, want)
+        out2 = torch.full_like(out, float("nan"))
+        ops.mesh_stencil(xl, band.dis, rows + 2, rows - 2, w, 2, bias=b, relu=True, out=out2[:, w:(rows - 1) * w])
+        ops.mesh_stencil(xl, band.dis, rows + 2, 1, w, 1, bias=b, relu=True, out=out2[:, :w])
+        ops.mesh_stencil(xl, band.dis, rows + 2, 1, w, rows, bias=b, relu=True, out=out2[:, (rows - 1) * w:])
+        assert torch.equal(out2, want)

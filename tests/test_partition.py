@@ -97,3 +97,35 @@ def _worker(rank, world, port, h, w, f, batch):
 def test_halo_exchange_gloo(world, batch):
     port = 29500 + (os.getpid() % 2000) + world * 7 + batch
     mp.spawn(_worker, args=(world, port, 8, 6, 4, batch), nprocs=world, join=True)
+
+
+def _band_worker(rank, world, port, h, w, f, batch):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, _, dis = orc.gcn_norm(orc.grid(h, w), h * w, dis_mode="exact")
+    band = partition.MeshBand(h, w, dis)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(batch, h * w, f, generator=gen)
+    xl = band.alloc(batch, f, torch.float32, "cpu")
+    band.owned(xl).copy_(x[:, band.r0 * w:(band.r0 + band.rows) * w])
+    band.exchange(xl)
+    want = torch.zeros(batch, (band.rows + 2) * w, f)
+    lo, hi = max(band.r0 - 1, 0), min(band.r0 + band.rows + 1, h)
+    want[:, (lo - (band.r0 - 1)) * w:(hi - (band.r0 - 1)) * w] = x[:, lo * w:hi * w]
+    assert torch.equal(xl, want), "band halo rows differ"
+    # bordered dis: element [r+1][c+1] = global dis of mesh row r0-1+r (0 outside the mesh)
+    d2 = dis.view(h, w)
+    for r in range(band.rows + 2):
+        gr = band.r0 - 1 + r
+        exp = d2[gr] if 0 <= gr < h else torch.zeros(w)
+        assert torch.equal(band.dis[r + 1, 1:w + 1], exp)
+    assert band.dis[0].abs().sum() == 0 and band.dis[:, 0].abs().sum() == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,batch", [(2, 1), (3, 2)])
+def test_mesh_band_exchange_gloo(world, batch):
+    port = 31500 + (os.getpid() % 2000) + world * 5 + batch
+    mp.spawn(_band_worker, args=(world, port, 9, 6, 4, batch), nprocs=world, join=True)
