@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu"]
-HEADERS = ["common.cuh", "tma.cuh"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu"]
+HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
 GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4

@@ -1,0 +1,361 @@
+// K2 (tensor-core path, CTA pairs): y = epi(x W^T + bias) for bf16 with tcgen05.mma.cta_group::2.
+//
+// Why pairs: k_linear_tc2 (one CTA per 128 x 256 tile) streams 48 KB of operands per 64-deep K
+// block into each SM for 512 cycles of MMA -- 94 B/clk/SM, more than an SM can pull from L2, and
+// ncu shows the tensor pipe 59 % active with the issuer waiting on full barriers.  Here two CTAs
+// of a cluster (one TPC) compute ONE 256 x BN tile: each CTA stages its own 128 rows of x and
+// only HALF of the W tile (BN/2 rows), the leader CTA issues M = 256 MMAs that read both CTAs'
+// shared memory, and each CTA's TMEM receives its own 128 accumulator rows.  Operand traffic per
+// SM drops to 32 KB per K block (64 B/clk).
+//
+// Roles per CTA (576 threads):
+//   warp 0 lane 0   TMA producer (both CTAs): A half + B half per K block, completing on the
+//                   LEADER's full[stage] barrier (cp.async.bulk.tensor ... .cta_group::2).
+//   warp 1 lane 0   MMA issuer (leader only): 4 x tcgen05.mma.cta_group::2 per K block;
+//                   tcgen05.commit ... multicast::cluster frees the stage in BOTH CTAs and
+//                   publishes the accumulator to both epilogues.
+//   warps 2..17     epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31, the 32-column sub-chunks
+//                   (w - 2) / 4, +4, ...: tcgen05.ld -> +bias (packed fp32x2, bias vector staged
+//                   in shared memory once) -> bf16 -> ReLU (bf16x2 max) -> 64B-swizzled st.shared
+//                   -> one TMA tensor store per warp and sub-chunk.  Two accumulators (2 x BN TMEM
+//                   columns) so the next tile's MMAs run under this tile's epilogue; the epilogue
+//                   warps of both CTAs arrive on the leader's tmem_empty barrier.
+// Measured at M = 896 292 (ms, cuBLAS matmul without epilogue in brackets): 64->1024 0.38 (0.31),
+// 1024->512 0.78 (0.72), 512->256 0.23 (0.23), 256->512 0.27 (0.28), 512->1024 0.81 (0.80),
+// 1024->64 0.31 (0.32).  The ring depth matters (3/4/5 stages: 0.92/0.81/0.77 ms at 1024->512), an
+// L2 prefetch of A ahead of the ring did not help and was removed; the 64->1024 case waits on
+// cp.async.bulk.wait_group.read (output write-back), independent of tile order.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tma.cuh"
+#include "tcgen05.cuh"
+
+namespace gwen {
+using namespace tc;
+namespace {
+
+constexpr int kEpiWarps = 16;
+constexpr int kTc3Threads = 64 + 32 * kEpiWarps;
+constexpr int kMaxStages = 8;
+
+struct Tc3Args {
+  const float* bias;
+  int64_t m;
+  int n, k_blocks, bn, stages, relu, bufs, row_major_tiles;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope): what must be ordered before the arrival is this
+  // warp's TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync already order;
+  // a .release.cluster here costs a MEMBAR.ALL.GPU per chunk (28 % of all stall samples in ncu).
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are counted on an mbarrier of either CTA of the pair.
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m, int c0, int c1,
+                                                 int c2, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(cluster_bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive (once all previously issued MMAs retire) on the barrier at this offset in BOTH CTAs.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"(uint16_t(3))
+      : "memory");
+}
+// Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M = 256 (pair), N = bn.
+__host__ __device__ constexpr uint32_t make_idesc_pair(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// {lo, hi} fp32 pair + {blo, bhi} (one FADD2), rounded to a bf16x2, optional ReLU on the pair.
+__device__ __forceinline__ uint32_t bias_pack(uint32_t lo, uint32_t hi, float blo, float bhi,
+                                              bool relu) {
+  uint64_t a, b, s;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "r"(lo), "r"(hi));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(blo), "f"(bhi));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(s) : "l"(a), "l"(b));
+  float f0, f1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(f0), "=f"(f1) : "l"(s));
+  __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
+  uint32_t u = *reinterpret_cast<uint32_t*>(&p);
+  if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(u) : "r"(0u));  // round then clamp == clamp then round
+  return u;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
+    k_linear_tc3(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                 const __grid_constant__ CUtensorMap ymap, Tc3Args g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar[2],
+      tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t a_bytes = BM * BK * 2, b_bytes = uint32_t(g.bn / 2) * BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t staging = base + uint32_t(g.stages) * stage_bytes;  // 16 warps x bufs x 2 KB
+  // the whole bias vector (n floats, zeros when absent) sits behind the staging buffers
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) +
+                                           size_t(kEpiWarps) * 2048u * size_t(g.bufs));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = g.n / g.bn;
+  const int n_sub = g.bn / 32;  // 32-column epilogue sub-chunks per tile
+  const int64_t m_blocks = (g.m + 2 * BM - 1) / (2 * BM);
+  const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  // Tile order.  row_major_tiles: a pair owns whole 256-row blocks (c, c + n_clusters, ..) and walks
+  // their N tiles one after the other, so it completes full output rows within a few tiles (DRAM
+  // pages are written once) and re-reads its A rows from L2.  Otherwise tiles are dealt round-robin
+  // with N fastest (better balance when there are few row blocks).
+  const int64_t my_tiles = g.row_major_tiles
+      ? (m_blocks > cluster_id ? ((m_blocks - 1 - cluster_id) / n_clusters + 1) * n_tiles : 0)
+      : (m_blocks * n_tiles > cluster_id ? (m_blocks * n_tiles - 1 - cluster_id) / n_clusters + 1 : 0);
+  auto tile_of = [&](int64_t idx, int& mb, int& nt) {
+    if (g.row_major_tiles) {
+      mb = int(cluster_id + (idx / n_tiles) * n_clusters);
+      nt = int(idx % n_tiles);
+    } else {
+      const int64_t t = cluster_id + idx * n_clusters;
+      mb = int(t / n_tiles);
+      nt = int(t % n_tiles);
+    }
+  };
+  const uint32_t tmem_cols = uint32_t(2 * g.bn);
+  const uint32_t epi_arrivals = 2u * 4u * uint32_t(n_sub < 4 ? n_sub : 4);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap);
+    tma_prefetch_desc(&ymap);
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), epi_arrivals);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < g.n; i += kTc3Threads) bias_s[i] = g.bias ? __ldg(g.bias + i) : 0.0f;
+  if (warp == 1) {  // the same warp of both CTAs allocates the pair's TMEM columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+      uint32_t it = 0;
+      for (int64_t idx = 0; idx < my_tiles; ++idx) {
+        int mb, nt;
+        tile_of(idx, mb, nt);
+        const int m0 = mb * (2 * BM) + int(rank) * BM;
+        const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const uint32_t s = it % uint32_t(g.stages), round = it / uint32_t(g.stages);
+          if (round > 0) mbar_wait(smem_u32(&empty_bar[s]), (round - 1) & 1u);
+          if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * stage_bytes);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          const uint32_t dst = base + s * stage_bytes;
+          tma_load_3d_pair(dst, &amap, kb * BK, m0, 0, bar);
+          tma_load_3d_pair(dst + a_bytes, &bmap, kb * BK, n0, 0, bar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {  // ===== MMA issuer (leader CTA) =====
+      const uint32_t idesc = make_idesc_pair(g.bn);
+      uint32_t it = 0, seq = 0;
+      for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
+        const uint32_t acc = seq & 1u, use = seq >> 1;
+        if (use > 0) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use - 1) & 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
+        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const uint32_t s = it % uint32_t(g.stages);
+          mbar_wait(smem_u32(&full_bar[s]), (it / uint32_t(g.stages)) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = base + s * stage_bytes;
+          const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(a_addr + a_bytes);
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk)
+            umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+                          (kb | kk) ? 1u : 0u);
+          umma_commit_pair(smem_u32(&empty_bar[s]));
+        }
+        umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..17: TMEM lanes 32*(warp%4) .. +31, 32-column sub-chunks g4, g4+4, .. =====
+    const int q = warp & 3, g4 = (warp - 2) >> 2;
+    const uint32_t my_stage = staging + uint32_t(warp - 2) * 2048u * uint32_t(g.bufs);  // 2 KB buffers
+    const uint32_t row_off = uint32_t(lane) * 64u;
+    const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
+    const bool relu = g.relu != 0;
+    const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
+    uint32_t seq = 0, buf = 0;
+    if (g4 < n_sub) {
+      for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
+        int mb, nt;
+        tile_of(idx, mb, nt);
+        const int m0 = mb * (2 * BM) + int(rank) * BM;
+        const int n0 = nt * g.bn;
+        const uint32_t acc = seq & 1u;
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
+        for (int sc = g4; sc < n_sub; sc += 4) {
+          const int c = sc * 32;
+          uint32_t r[32];
+          tmem_ld32_nowait(t_addr + uint32_t(c), r);
+          // the staging buffer we are about to overwrite must have been read by its TMA store
+          if (lane == 0) {
+            if (g.bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (sc + 4 >= n_sub) {  // last TMEM read of this tile by this warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? empty_remote1 : empty_remote0);
+          }
+          __syncwarp();
+          const uint32_t sbuf = my_stage + buf * 2048u + row_off;
+          // bias slice of this sub-chunk (same address for every lane: broadcast LDS.128)
+          const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // 4 chunks of 8 columns = 16 bytes
+            const float4 b0 = bp[2 * j], b1 = bp[2 * j + 1];
+            uint4 o;
+            o.x = bias_pack(r[8 * j + 0], r[8 * j + 1], b0.x, b0.y, relu);
+            o.y = bias_pack(r[8 * j + 2], r[8 * j + 3], b0.z, b0.w, relu);
+            o.z = bias_pack(r[8 * j + 4], r[8 * j + 5], b1.x, b1.y, relu);
+            o.w = bias_pack(r[8 * j + 6], r[8 * j + 7], b1.z, b1.w, relu);
+            sts_v4(sbuf + ((uint32_t(j) ^ sw) << 4), o);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&ymap, my_stage + buf * 2048u, n0 + c, m0 + q * 32, 0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          buf = (buf + 1u) & uint32_t(g.bufs - 1);
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading our operands / arriving on our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out) {
+  static const bool disabled = getenv("GWEN_TC_NO_PAIR") != nullptr;
+  return !disabled && n_out % 64 == 0 && n_out <= 8192 && m >= 256 && k >= 8 && sm_count() % 2 == 0;
+}
+
+int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
+                        int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
+                        cudaStream_t st) {
+  int bn = 0;
+  for (int c : {256, 128, 64})
+    if (n_out % c == 0) { bn = c; break; }
+  if (!bn) return set_err(GWEN_E_NOSUPPORT, "tcgen05 pair GEMM needs n_out %% 64 == 0");
+  CUtensorMap amap, bmap, ymap;
+  int rc = make_tensor_map_3d(&amap, x, GWEN_BF16, k, m, 1, ldx, 0, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  rc = make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  rc = make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, 1, ldy, 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != GWEN_OK) return rc;
+  const int k_blocks = static_cast<int>(ceil_div(k, BK));
+  const size_t stage_bytes = size_t(BM + bn / 2) * BK * 2;
+  static const int bufs = [] {
+    const char* v = getenv("GWEN_TC3_BUFS");
+    return v && atoi(v) == 2 ? 2 : 1;
+  }();
+  const size_t staging_bytes = size_t(kEpiWarps) * bufs * 2048 + align_up(size_t(n_out) * 4, 1024);
+  static const int stage_cap = [] {
+    const char* v = getenv("GWEN_TC3_STAGES");
+    return v ? std::max(2, std::min(kMaxStages, atoi(v))) : kMaxStages;
+  }();
+  int stages = static_cast<int>(std::min<size_t>(stage_cap, (226 * 1024 - staging_bytes - 1024) / stage_bytes));
+  if (stages < 2) return set_err(GWEN_E_NOSUPPORT, "tile does not fit in shared memory");
+  // >= 120 KB keeps one CTA per SM (a pair owns up to all 512 TMEM columns of both SMs)
+  const size_t smem = std::max<size_t>(stages * stage_bytes + staging_bytes + 1024, 120 * 1024);
+  const int64_t total = ceil_div(m, 2 * BM) * (n_out / bn);
+  const int pairs = static_cast<int>(std::min<int64_t>(total, std::max(1, (sm_count() - sm_reserve()) / 2)));
+  static const int order_env = [] {
+    const char* v = getenv("GWEN_TC3_ORDER");
+    return v ? atoi(v) : -1;
+  }();
+  // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
+  const int row_major = order_env >= 0 ? order_env : 0;
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major};
+  GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);
+  GWEN_LAUNCH_CHECK("k_linear_tc3");
+  return GWEN_OK;
+}
+
+}  // namespace gwen

@@ -255,7 +255,7 @@ def test_linear_fp32(dev, m, k, n):
 
 @pytest.mark.parametrize("m,k,n", [(300, 64, 1024), (1000, 1024, 512), (640, 512, 256), (130, 40, 24),
                                    (257, 72, 96), (643, 1024, 64), (5, 256, 512), (4096, 256, 256),
-                                   (20000, 128, 128)])
+                                   (20000, 128, 128), (40000, 192, 1024), (70001, 1024, 256)])
 def test_linear_bf16(dev, m, k, n):
     """bf16 projection (tcgen05 path when K % 8 == 0 and N % 32 == 0, CUDA-core path otherwise)
     against a plain fp64 reference of the same bf16-rounded operands."""
