@@ -11,8 +11,9 @@ Metric: message-passing edges/s = E' x steps / time (whole job, all ranks).
   python bench.py --impl reference [--gpus N] ...                  # the reference's CPU path
 
 N > 1 (launched with torch.distributed.run, one rank per GPU): WEAK scaling -- every rank owns a
-582 x 390 row band of a (582 N) x 390 mesh and fetches its one-row halos from the neighbouring
-ranks over NCCL before each aggregation (gwen_b200/partition.py).
+582 x 390 row band of a (582 N) x 390 mesh.  The one-row halos are fetched INSIDE the aggregation
+kernel from the neighbours' buffers over NVLink peer memory (gwen_grid_stencil_peer_fwd,
+partition.PeerMeshBand); --halo nccl selects the NCCL send/recv exchange (partition.MeshBand).
 
 Timing: W untimed steps, then exactly K steps bracketed by barrier + synchronize, CUDA events on
 the launching stream, max over ranks.  Inputs + outputs (465 MB) exceed the 126 MB L2, so no
@@ -47,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: halo exchange inside the kernel over peer memory, or NCCL send/recv")
     return ap.parse_args()
 
 
@@ -204,16 +207,20 @@ def run_ours(args):
         x = torch.randn(n_own, FEAT, generator=gen).to(dev)
         x_own = x
     else:
-        band = partition.MeshBand(gh, W, g_global.dis)
+        band = partition.PeerMeshBand(gh, W, g_global.dis) if args.halo == "peer" else \
+            partition.MeshBand(gh, W, g_global.dis)
         n_own, n_local = band.n_own, band.n_local
         ranges = partition.band_ranges(gh, W, world)
         rp = g_global.rowptr
         msgs_local = int((rp[ranges[rank].stop] - rp[ranges[rank].start]).item())
-        launches_per_step = 3  # interior + first-row + last-row stencil launches (halos move in place)
+        # peer: ONE launch (halo fetch inside); nccl: interior + first-row + last-row launches
+        launches_per_step = 1 if args.halo == "peer" else 3
         del g_global, ei
-        x = band.alloc(1, FEAT, torch.float32, dev)[0]
-        x_own = band.owned(x)
+        xs = [band.alloc(1, FEAT, torch.float32, dev) for _ in range(2)]   # ping-pong for the e2e leg
+        x = xs[0]
+        x_own = band.owned(x[0])
         x_own.copy_(torch.randn(n_own, FEAT, generator=gen).to(dev))
+        band.owned(xs[1][0]).copy_(x_own)
     out = torch.empty(n_own, FEAT, device=dev)
 
     def step():
@@ -233,9 +240,9 @@ def run_ours(args):
     sync_all()
     step_mode = "eager launches"
     if band is not None:
-        # The partitioned step is ~8 host-side operations (fork/join events, halo packs, NCCL
-        # send/recv, interior + boundary launches) for ~120 us of GPU work: capture it once in a
-        # CUDA graph and replay it, so the GPU is not waiting on the Python launch path.
+        # Capture the partitioned step once in a CUDA graph and replay it, so that all ranks' launches
+        # are queued ahead of the GPU (peer: the ranks' kernels wait on one another's flags; nccl:
+        # the step is ~8 host-side operations for ~100 us of GPU work).
         eager_step = step
         try:
             cap = torch.cuda.Stream()
@@ -279,7 +286,7 @@ def run_ours(args):
         if band is None:
             ops.aggregate(graph, x, bias, kernel="stencil", out=out)
         else:
-            ops.mesh_stencil(x, band.dis, band.rows + 2, band.rows, W, 1, bias=bias, out=out)
+            ops.mesh_stencil(x[0, :band.n_local], band.dis, band.rows + 2, band.rows, W, 1, bias=bias, out=out)
         b.record()
         per.append((a, b))
     torch.cuda.synchronize()
@@ -296,11 +303,18 @@ def run_ours(args):
     with torch.no_grad():
         conv.bias.copy_(bias)
 
+    e2e_i = [0]
+
     def e2e_step():
-        x_own.copy_(x_host, non_blocking=True)
         if band is not None:
-            y = band.aggregate(x, conv.bias)
+            # a neighbour reads this rank's boundary rows during ITS launch: alternate two buffers so
+            # that the next step's H2D copy never overwrites rows a neighbour may still be reading
+            xb = xs[e2e_i[0] & 1]
+            e2e_i[0] += 1
+            band.owned(xb[0]).copy_(x_host, non_blocking=True)
+            y = band.aggregate(xb, conv.bias)
         else:
+            x_own.copy_(x_host, non_blocking=True)
             y = conv.propagate(graph, x)
         out_host.copy_(y.view(n_own, FEAT), non_blocking=True)
 
@@ -327,7 +341,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + "; weak scaling: one 582x390 "
-                       "row band per rank of a %dx390 mesh, one-row halo exchange (NCCL send/recv, overlapped with the interior tiles) per step" % gh,
+                       "row band per rank of a %dx390 mesh, one-row halo exchange per step (%s)" % (gh, "inside the aggregation kernel: one warp per CTA pulls the neighbours' boundary rows over NVLink peer memory under the interior tiles, device-side flags" if args.halo == "peer" else "NCCL send/recv on a side stream under the interior rows"),
                        "l2": "inputs+outputs 465 MB per rank > 126 MB L2, no explicit flush",
                        "step_launch": step_mode,
                        "kernel": "k_grid_stencil (mesh fast path: 8x32 tiles, one 4-D TMA box per tile/slab, "

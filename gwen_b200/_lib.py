@@ -63,6 +63,13 @@ class TilePlanStruct(C.Structure):
                 ("tmsg_base", C.c_void_p)]
 
 
+class HaloPeersStruct(C.Structure):
+    """gwen_halo_peers (include/gwen_b200.h)."""
+    _fields_ = [("up_row", C.c_void_p), ("down_row", C.c_void_p), ("up_bstride", C.c_int64),
+                ("down_bstride", C.c_int64), ("up_flag", C.c_void_p), ("down_flag", C.c_void_p),
+                ("ctl", C.c_void_p)]
+
+
 _p, _i64, _i32, _u32, _int, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_int, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/gwen_b200.h declares.
@@ -87,6 +94,8 @@ PROTOTYPES = {
                                         _p]),
     "gwen_grid_stencil_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                      _i64, _i64, _int, _p, _int, _i32, _i32, _p]),
+    "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                          _int, _p, _int, _i32, _i32, C.POINTER(HaloPeersStruct), _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,

@@ -110,12 +110,47 @@ struct StencilArgs {
   uint32_t x_bytes, dis_pitch, stage_bytes;  // bytes of the x box, dis box row pitch, one stage
   const float* disb;       // zero-bordered dis, [hs + 2][disb_pitch]
   int64_t disb_pitch;
+  // peer-halo mode (gwen_grid_stencil_peer_fwd): the kernel fetches its two halo rows itself
+  int peer;                 // 0 = plain launch
+  unsigned char* x_base;    // local x (halo row 0 at offset 0 of each batch slice)
+  const unsigned char* up_src;    // neighbour rows to copy (device pointers into PEER memory)
+  const unsigned char* down_src;
+  int64_t x_bstride_bytes, up_bstride_bytes, down_bstride_bytes, row_bytes, bottom_off_bytes;
+  uint32_t* flag_up_remote;   // where this rank announces "my x is ready" to the neighbours
+  uint32_t* flag_down_remote;
+  uint32_t* ctl;              // local control words, see gwen_halo_peers
 };
+
+// control words of the peer-halo protocol (ctl[] in local device memory, zero-initialised)
+enum { CTL_FROM_UP = 0, CTL_FROM_DOWN = 1, CTL_EPOCH = 2, CTL_HALO_DONE = 3, CTL_CTAS_DONE = 4 };
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_peer_v4(const void* p) {  // uncached at every level we control
+  uint4 r;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
 
 // LPR lanes cover one slab (LPR * 16 bytes); 32/LPR sub-warps per warp, each walks one unit
 // (destination row r of the tile, columns [seg*SEG, seg*SEG + SEG)).
 template <typename T, int LPR>
-__global__ void __launch_bounds__(544, 1)
+__global__ void __launch_bounds__(576, 1)
     k_grid_stencil(const __grid_constant__ CUtensorMap xmap, StencilArgs a) {
   constexpr int VN = V16<T>::N;
   constexpr int RPW = 32 / LPR;
@@ -125,7 +160,8 @@ __global__ void __launch_bounds__(544, 1)
   const int ns = a.num_stages;
   const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int ncw = nwarps - 1;
+  const int ncw = nwarps - (a.peer ? 2 : 1);  // consumers | producer warp | (peer mode) halo warp
+  const uint32_t epoch1 = a.peer ? *reinterpret_cast<volatile uint32_t*>(a.ctl + CTL_EPOCH) + 1u : 0u;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&xmap);
     for (int i = 0; i < ns; ++i) {
@@ -142,12 +178,69 @@ __global__ void __launch_bounds__(544, 1)
   const uint32_t slab_bytes = a.slab_elems * sizeof(T);
   const uint32_t srow_bytes = uint32_t(a.tw + 2) * slab_bytes;  // one staged mesh row
 
-  if (warp == ncw) {
+  // Peer mode walks the interior tile rows first and the two tile rows that read a halo row last
+  // (tile row 0, then the bottom one), so the halo fetch runs under the interior work.
+  const int tiles_y = a.num_tiles / a.tiles_x;
+  const int n_interior = tiles_y > 2 ? (tiles_y - 2) * a.tiles_x : 0;
+  auto tile_at = [&](int seq) {
+    if (!a.peer) return seq;
+    if (seq < n_interior) return seq + a.tiles_x;
+    const int r = seq - n_interior;              // boundary tiles
+    if (r < a.tiles_x) return r;                 // tile row 0
+    return (tiles_y - 1) * a.tiles_x + (r - a.tiles_x);
+  };
+
+  if (warp == ncw + 1) {
+    // ===== halo warp (peer mode): announce, then pull this CTA's share of both halo rows =====
+    if (blockIdx.x == 0 && lane == 0) {
+      __threadfence_system();
+      if (a.flag_up_remote) st_release_sys(a.flag_up_remote, epoch1);
+      if (a.flag_down_remote) st_release_sys(a.flag_down_remote, epoch1);
+    }
+    const int64_t units_row = a.row_bytes / 16;
+    const int64_t units = units_row * a.batch;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const unsigned char* src = side ? a.down_src : a.up_src;
+      if (!src) continue;
+      if (lane == 0)
+        while (int32_t(ld_acquire_sys(a.ctl + (side ? CTL_FROM_DOWN : CTL_FROM_UP)) - epoch1) < 0)
+          __nanosleep(64);
+      __syncwarp();
+      const int64_t sb = side ? a.down_bstride_bytes : a.up_bstride_bytes;
+      unsigned char* dst = a.x_base + (side ? a.bottom_off_bytes : 0);
+      constexpr int U = 4;
+      for (int64_t u0 = (int64_t(blockIdx.x) * 32 + lane); u0 < units; u0 += int64_t(gridDim.x) * 32 * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int64_t u = u0 + int64_t(k) * gridDim.x * 32;
+          if (u < units) v[k] = ld_peer_v4(src + (u / units_row) * sb + (u % units_row) * 16);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int64_t u = u0 + int64_t(k) * gridDim.x * 32;
+          if (u < units)
+            *reinterpret_cast<uint4*>(dst + (u / units_row) * a.x_bstride_bytes + (u % units_row) * 16) = v[k];
+        }
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) red_release_gpu_add(a.ctl + CTL_HALO_DONE, 1u);
+  } else if (warp == ncw) {
     if (lane == 0) {  // ===== producer =====
       int st = 0;
       uint32_t round = 0;
+      bool halo_ready = !a.peer;
       for (int64_t it = 0; it < n_items; ++it) {
-        const int t = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+        const int seq = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+        const int t = tile_at(seq);
+        if (!halo_ready && seq >= n_interior) {  // first tile that reads a halo row
+          while (ld_acquire_gpu(a.ctl + CTL_HALO_DONE) < gridDim.x) __nanosleep(32);
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores -> TMA reads
+          halo_ready = true;
+        }
         const int rem = int(it % per_tile);
         const int b = rem / a.slabs, slab = rem % a.slabs;
         const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
@@ -165,9 +258,7 @@ __global__ void __launch_bounds__(544, 1)
         if (++st == ns) { st = 0; ++round; }
       }
     }
-    return;
-  }
-
+  } else {
   // ===== consumers =====
   const int sub = lane / LPR, l = lane % LPR;
   const int nseg = a.tw / SEG;
@@ -175,7 +266,7 @@ __global__ void __launch_bounds__(544, 1)
   int st = 0;
   uint32_t round = 0;
   for (int64_t it = 0; it < n_items; ++it) {
-    const int t = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+    const int t = tile_at(int(blockIdx.x) + int(it / per_tile) * int(gridDim.x));
     const int rem = int(it % per_tile);
     const int b = rem / a.slabs, slab = rem % a.slabs;
     const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
@@ -234,6 +325,21 @@ __global__ void __launch_bounds__(544, 1)
     if (lane == 0) mbar_arrive(smem_u32(&empty_bar[st]));
     if (++st == ns) { st = 0; ++round; }
   }
+  }  // roles
+  if (a.peer) {
+    // last CTA out re-arms the protocol for the next launch: every CTA has read the epoch and
+    // passed (or never needed) the halo wait by the time all of them have finished.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(a.ctl + CTL_CTAS_DONE, 1u) == gridDim.x - 1) {
+        a.ctl[CTL_HALO_DONE] = 0;
+        a.ctl[CTL_CTAS_DONE] = 0;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(a.ctl + CTL_EPOCH) = epoch1;
+      }
+    }
+  }
 }
 
 inline int env_int2(const char* name, int dflt, int lo, int hi) {
@@ -250,7 +356,7 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
                                  static_cast<int>(smem)));
   const int grid = std::min(a.num_tiles, std::max(1, sm_count() - sm_reserve()));
   // consumer sub-warps = TH * tw / SEG units when possible: 16 consumer warps + 1 producer warp
-  kern<<<grid, 544, smem, st>>>(xmap, a);
+  kern<<<grid, a.peer ? 576 : 544, smem, st>>>(xmap, a);
   GWEN_LAUNCH_CHECK("k_grid_stencil");
   return GWEN_OK;
 }
@@ -260,12 +366,11 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
 
 using namespace gwen;
 
-extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded,
-                                     int64_t dis_pitch, int64_t batch, int64_t hs, int64_t hd,
-                                     int64_t w, int64_t row_off, int64_t feat, int64_t ldx,
-                                     int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
-                                     const float* bias, int epilogue, int32_t slab_elems,
-                                     int32_t tile_w, void* stream) {
+static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_t dis_pitch,
+                       int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
+                       int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo, int64_t o_bstride,
+                       int dtype, const float* bias, int epilogue, int32_t slab_elems,
+                       int32_t tile_w, const gwen_halo_peers* peers, void* stream) {
   GWEN_CHECK_ARG(batch >= 0 && hs >= 0 && hd >= 0 && w >= 0 && feat >= 0, "negative size");
   if (batch == 0 || hd == 0 || w == 0 || feat == 0) return GWEN_OK;
   GWEN_CHECK_ARG(x && out && dis_padded, "null pointer");
@@ -315,11 +420,29 @@ extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_
     if (r != CUDA_SUCCESS) return set_err(GWEN_E_CUDA, "x tensor map encode failed (%d)", int(r));
   }
   const int tiles_x = static_cast<int>(ceil_div(w, tw)), tiles_y = static_cast<int>(ceil_div(hd, TH));
-  StencilArgs a{out, bias, batch, feat, ldo, o_bstride, static_cast<int>(hd), static_cast<int>(w),
+  StencilArgs a{};
+  a = StencilArgs{out, bias, batch, feat, ldo, o_bstride, static_cast<int>(hd), static_cast<int>(w),
                 static_cast<int>(row_off), tw, tiles_x, tiles_x * tiles_y,
                 static_cast<int>(ceil_div(feat, slab)), slab, (epilogue & GWEN_EPI_RELU) ? 1 : 0, ns,
                 static_cast<uint32_t>(size_t(TH + 2) * (tw + 2) * lpr * 16), dis_box_w * 4,
                 static_cast<uint32_t>(stage_for(lpr)), dis_padded, dis_pitch};
+  if (peers) {
+    // x is this rank's band [B][hd + 2][w][feat]: local row 0 / hd + 1 are the halo rows
+    GWEN_CHECK_ARG(row_off == 1 && hs == hd + 2 && ldx == feat, "peer mode needs x = [B, hd + 2, w, feat], row_off 1");
+    GWEN_CHECK_ARG(peers->ctl && aligned16(peers->up_row) && aligned16(peers->down_row), "bad halo peers");
+    a.peer = 1;
+    a.x_base = static_cast<unsigned char*>(const_cast<void*>(x));
+    a.up_src = static_cast<const unsigned char*>(peers->up_row);
+    a.down_src = static_cast<const unsigned char*>(peers->down_row);
+    a.row_bytes = w * feat * esz;
+    a.x_bstride_bytes = (batch > 1 ? x_bstride : hs * w * ldx) * esz;
+    a.up_bstride_bytes = peers->up_bstride * esz;
+    a.down_bstride_bytes = peers->down_bstride * esz;
+    a.bottom_off_bytes = (hd + 1) * a.row_bytes;
+    a.flag_up_remote = peers->up_flag;
+    a.flag_down_remote = peers->down_flag;
+    a.ctl = peers->ctl;
+  }
   if (dis_pitch < int64_t(tiles_x - 1) * tw + dis_box_w)
     return set_err(GWEN_E_BADARG, "bordered dis pitch %lld < %lld needed for tile width %d",
                    (long long)dis_pitch, (long long)(int64_t(tiles_x - 1) * tw + dis_box_w), tw);
@@ -333,4 +456,25 @@ extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_
   if (lpr == 32) return launch_stencil<__nv_bfloat16, 32>(xmap, a, smem, st);
   if (lpr == 16) return launch_stencil<__nv_bfloat16, 16>(xmap, a, smem, st);
   return launch_stencil<__nv_bfloat16, 8>(xmap, a, smem, st);
+}
+
+extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded,
+                                     int64_t dis_pitch, int64_t batch, int64_t hs, int64_t hd,
+                                     int64_t w, int64_t row_off, int64_t feat, int64_t ldx,
+                                     int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
+                                     const float* bias, int epilogue, int32_t slab_elems,
+                                     int32_t tile_w, void* stream) {
+  return stencil_fwd(x, out, dis_padded, dis_pitch, batch, hs, hd, w, row_off, feat, ldx, x_bstride,
+                     ldo, o_bstride, dtype, bias, epilogue, slab_elems, tile_w, nullptr, stream);
+}
+
+extern "C" int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded,
+                                          int64_t dis_pitch, int64_t batch, int64_t hd, int64_t w,
+                                          int64_t feat, int64_t x_bstride, int64_t ldo,
+                                          int64_t o_bstride, int dtype, const float* bias,
+                                          int epilogue, int32_t slab_elems, int32_t tile_w,
+                                          const gwen_halo_peers* peers, void* stream) {
+  GWEN_CHECK_ARG(peers != nullptr, "null halo peers");
+  return stencil_fwd(x, out, dis_padded, dis_pitch, batch, hd + 2, hd, w, 1, feat, feat, x_bstride,
+                     ldo, o_bstride, dtype, bias, epilogue, slab_elems, tile_w, peers, stream);
 }

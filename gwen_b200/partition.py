@@ -17,13 +17,16 @@ from __future__ import annotations
 
 from typing import List, Optional, Sequence
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
 from . import ops
 from .graph import GraphCSR, bordered_dis
 
-__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator", "MeshBand"]
+__all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator", "MeshBand",
+           "PeerMeshBand"]
 
 
 def band_ranges(height: int, width: int, world_size: int) -> List[range]:
@@ -299,4 +302,82 @@ class MeshBand:
         cur.wait_event(done)
         ops.mesh_stencil(x3, self.dis, rows + 2, 1, w, 1, out=o3[:, :w], **kw)
         ops.mesh_stencil(x3, self.dis, rows + 2, 1, w, rows, out=o3[:, (rows - 1) * w:], **kw)
+        return out
+
+
+class PeerMeshBand(MeshBand):
+    """:class:`MeshBand` whose halo exchange happens INSIDE the aggregation kernel, over NVLink peer
+    memory (``gwen_grid_stencil_peer_fwd``): no NCCL call, no pack kernels, one launch per step.
+
+    Feature buffers come from ``alloc`` (CUDA symmetric memory, ``torch.distributed._symmetric_memory``):
+    every rank allocates the same shapes in the same order, which gives each rank device pointers
+    to its neighbours' buffers.  The neighbours' boundary rows are pulled by one extra warp per CTA
+    while the interior tile rows are aggregated; flags in symmetric memory order the exchange
+    (see include/gwen_b200.h).  Results are bitwise equal to ``MeshBand.aggregate``.
+    """
+
+    def __init__(self, height: int, width: int, dis_global: torch.Tensor, group=None,
+                 rank: Optional[int] = None, world: Optional[int] = None):
+        super().__init__(height, width, dis_global, group=group, sm_reserve=0, rank=rank, world=world)
+        import torch.distributed._symmetric_memory as symm
+        self._symm = symm
+        self._group = group if group is not None else dist.group.WORLD
+        dev = dis_global.device
+        # rows owned by every rank (the neighbours' layouts differ by at most one row)
+        self._rows_of = [len(r) // width for r in band_ranges(height, width, self.world)]
+        self._ctl = symm.empty(64, dtype=torch.int32, device=dev)
+        self._ctl.zero_()
+        self._ctl_hdl = symm.rendezvous(self._ctl, self._group)
+        self._bufs = {}
+        torch.cuda.synchronize(dev)
+        dist.barrier(self._group)
+
+    def alloc(self, batch: int, feat: int, dtype, device) -> torch.Tensor:
+        """Zero-initialised SYMMETRIC local feature buffer [batch, n_local_max, feat] (collective:
+        all ranks call it with the same arguments).  Sized for the tallest band so that every rank's
+        allocation has the same shape; use ``[:, :n_local]``."""
+        rows_max = max(self._rows_of)
+        t = self._symm.empty((batch, (rows_max + 2) * self.W, feat), dtype=dtype, device=device)
+        t.zero_()
+        hdl = self._symm.rendezvous(t, self._group)
+        self._bufs[t.data_ptr()] = (t, hdl)
+        torch.cuda.synchronize(device)
+        dist.barrier(self._group)
+        return t
+
+    def _peers(self, x3: torch.Tensor):
+        from . import _lib
+        t, hdl = self._bufs[x3.data_ptr()]
+        esz, w, f = x3.element_size(), self.W, x3.shape[-1]
+        bstride = t.stride(0)
+        ctl = self._ctl_hdl.buffer_ptrs
+        up_row = down_row = up_flag = down_flag = None
+        if self.up is not None:      # its last owned row = local row rows_up
+            up_row = hdl.buffer_ptrs[self.up] + self._rows_of[self.up] * w * f * esz
+            up_flag = ctl[self.up] + 4 * 1          # I am its DOWN neighbour
+        if self.down is not None:    # its first owned row = local row 1
+            down_row = hdl.buffer_ptrs[self.down] + w * f * esz
+            down_flag = ctl[self.down] + 4 * 0      # I am its UP neighbour
+        return _lib.HaloPeersStruct(up_row, down_row, bstride, bstride, up_flag, down_flag,
+                                    self._ctl.data_ptr())
+
+    def aggregate(self, x_local: torch.Tensor, bias=None, relu: bool = False, out=None,
+                  overlap: bool = True) -> torch.Tensor:
+        from . import _lib
+        from ._lib import check, lib
+        x3 = x_local if x_local.dim() == 3 else x_local.unsqueeze(0)
+        if x3.data_ptr() not in self._bufs:
+            raise RuntimeError("PeerMeshBand.aggregate needs a buffer from PeerMeshBand.alloc (symmetric memory)")
+        b, _, f = x3.shape
+        if out is None:
+            out = torch.empty((b, self.n_own, f), dtype=x3.dtype, device=x3.device)
+        o3 = out if out.dim() == 3 else out.unsqueeze(0)
+        peers = self._peers(x3)
+        bias32 = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(x3.device):
+            check(lib().gwen_grid_stencil_peer_fwd(
+                x3.data_ptr(), o3.data_ptr(), self.dis.data_ptr(), self.dis.shape[1], b, self.rows, self.W, f,
+                x3.stride(0), f, o3.stride(0) if b > 1 else self.n_own * f, ops.dtype_code(x3.dtype),
+                None if bias32 is None else bias32.data_ptr(), _lib.EPI_RELU if relu else 0, 0, 0,
+                C.byref(peers), torch.cuda.current_stream().cuda_stream), "gwen_grid_stencil_peer_fwd")
         return out

@@ -199,6 +199,39 @@ int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded, int
                           int64_t o_bstride, int dtype, const float* bias, int epilogue,
                           int32_t slab_elems, int32_t tile_w, void* stream);
 
+/* K1s + halo exchange in ONE kernel (multi-GPU row bands, SURVEY.md section 8e: no reference
+ * counterpart -- the reference runs identical replicas).  x is this rank's band
+ * [B, hd + 2, w, feat]: local row 0 and row hd + 1 are the halo rows, rows 1 .. hd are owned.  The
+ * launch (1) stores its epoch into the neighbours' flag words (peer memory over NVLink), (2) one
+ * extra warp per CTA waits for the neighbours' flags and copies its share of their boundary rows
+ * from PEER memory into the local halo rows while the other warps aggregate the interior tile
+ * rows, (3) the tile rows that read a halo row are processed last, after all CTAs have published
+ * their share.  Results are bitwise equal to gwen_grid_stencil_fwd on exchanged halos.
+ * All ranks must launch the same sequence of peer calls (epochs are counted on the device, so a
+ * CUDA-graph replay works).  The neighbour reads this rank's rows 1 and hd of x during ITS launch
+ * of the same epoch: do not overwrite x before the next peer launch (ping-pong two buffers).
+ * up_row / down_row : the up neighbour's LAST owned row / the down neighbour's FIRST owned row
+ *                     (pointers into the neighbour's x, mapped into this process), NULL at the
+ *                     mesh edge (the local halo row must then be zero)
+ * up/down_bstride   : the neighbour's batch stride in elements
+ * up_flag/down_flag : address (peer memory) of the neighbour's ctl[1] / ctl[0]
+ * ctl               : >= 8 zero-initialised uint32 in LOCAL device memory, owned by the protocol:
+ *                     [0] epoch announced by the up neighbour, [1] by the down neighbour,
+ *                     [2] epochs completed, [3] CTAs that published their halo share, [4] CTAs done */
+typedef struct gwen_halo_peers {
+  const void* up_row;
+  const void* down_row;
+  int64_t up_bstride, down_bstride;
+  uint32_t* up_flag;
+  uint32_t* down_flag;
+  uint32_t* ctl;
+} gwen_halo_peers;
+int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded, int64_t dis_pitch,
+                               int64_t batch, int64_t hd, int64_t w, int64_t feat,
+                               int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
+                               const float* bias, int epilogue, int32_t slab_elems, int32_t tile_w,
+                               const gwen_halo_peers* peers, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
  * SURVEY.md table 2.3 row 6) and, through the epilogue, the bias add and ReLU when the

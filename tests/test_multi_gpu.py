@@ -1,0 +1,27 @@
+"""Multi-GPU parity of the in-kernel peer-memory halo exchange (PeerMeshBand): every rank's band of
+the stencil aggregation is BITWISE equal to the single-GPU result, over several epochs with changing
+inputs (protocol re-arming), for ragged band heights and batch > 1.  Needs >= 2 GPUs (skipped on a
+single-GPU box; the host logic of the partition is covered by the gloo tests in test_partition.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_peer_halo_stencil_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "peer_band_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["bitwise_equal_to_single_gpu"] is True
