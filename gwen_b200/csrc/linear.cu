@@ -25,6 +25,18 @@ int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t
                        int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
                        cudaStream_t st);
 
+int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldw,
+                              int64_t lddx, const void* dy, const void* w, const void* dx);
+int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
+                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st);
+
+// linear_wgrad_tc.cu
+int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
+                              const void* dy, const void* x);
+int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out);
+int linear_tc_wgrad_bf16(const void* dy, const void* x, float* part, int64_t m, int64_t k_in,
+                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st);
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
@@ -253,6 +265,76 @@ __global__ void __launch_bounds__(256) k_bias_partial(const T* __restrict__ dy, 
 
 constexpr int64_t kBiasChunk = 2048;
 
+// Fused epilogue backward: dz = dy * (y > 0) (written out of place; skipped when y == nullptr) and
+// the per-chunk column sums of dz for the bias gradient, in ONE pass over 16-byte vectors.
+// Thread t owns column group t % groups (groups = feat / VN divides 256) and the rows
+// r0 + t / groups, + 256 / groups, ...: sums in a fixed order, then a fixed-order cross-thread sum
+// in shared memory -> deterministic.
+template <typename T>
+__global__ void __launch_bounds__(256) k_relu_bias_bwd(const T* __restrict__ y,
+                                                       const T* __restrict__ dy, T* __restrict__ dz,
+                                                       int64_t rows, int groups, int64_t chunk,
+                                                       float* __restrict__ part) {
+  constexpr int VN = 16 / sizeof(T);
+  __shared__ float s[256][VN + 1];
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups, rstep = 256 / groups;
+  const int64_t r0 = int64_t(blockIdx.x) * chunk, r1 = min(rows, r0 + chunk);
+  const int64_t feat = int64_t(groups) * VN;
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] = 0.0f;
+  for (int64_t r = r0 + rl; r < r1; r += rstep) {
+    const int64_t off = r * feat + int64_t(cg) * VN;
+    uint4 d = __ldg(reinterpret_cast<const uint4*>(dy + off));
+    if (y) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + off));
+      if constexpr (sizeof(T) == 4) {
+        if (!(__uint_as_float(v.x) > 0.0f)) d.x = 0u;
+        if (!(__uint_as_float(v.y) > 0.0f)) d.y = 0u;
+        if (!(__uint_as_float(v.z) > 0.0f)) d.z = 0u;
+        if (!(__uint_as_float(v.w) > 0.0f)) d.w = 0u;
+      } else {
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+        uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 > 0  <=>  sign clear and magnitude non-zero (not NaN-safe, as relu)
+          const uint32_t lo = vv[i] & 0xffffu, hi = vv[i] >> 16;
+          const uint32_t mlo = (lo != 0u && lo < 0x8000u) ? 0xffffu : 0u;
+          const uint32_t mhi = (hi != 0u && hi < 0x8000u) ? 0xffff0000u : 0u;
+          dd[i] &= (mlo | mhi);
+        }
+        d = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+      }
+      *reinterpret_cast<uint4*>(dz + off) = d;
+    }
+    if (part) {
+      if constexpr (sizeof(T) == 4) {
+        acc[0] += __uint_as_float(d.x); acc[1] += __uint_as_float(d.y);
+        acc[2] += __uint_as_float(d.z); acc[3] += __uint_as_float(d.w);
+      } else {
+        const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += __uint_as_float(dd[i] << 16);
+          acc[2 * i + 1] += __uint_as_float(dd[i] & 0xffff0000u);
+        }
+      }
+    }
+  }
+  if (!part) return;
+#pragma unroll
+  for (int k = 0; k < VN; ++k) s[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < groups) {
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      float t = 0.0f;
+      for (int j = 0; j < rstep; ++j) t += s[j * groups + threadIdx.x][k];
+      part[int64_t(blockIdx.x) * feat + int64_t(threadIdx.x) * VN + k] = t;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace gwen
 
@@ -289,6 +371,8 @@ extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx
   GWEN_CHECK_ARG(dy && weight && dx, "null pointer");
   GWEN_CHECK_ARG(lddy >= n_out && ldw >= k && lddx >= k, "row pitch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == GWEN_BF16 && linear_tc_dgrad_supported(m, k, n_out, lddy, ldw, lddx, dy, weight, dx))
+    return linear_tc_dgrad_bf16(dy, weight, dx, m, k, n_out, lddy, ldw, lddx, st);
   // dx[m, kk] = sum_n dy[m, n] * W[n, kk]:  A = dy (R-major), B(j=kk, r=n) = W[r*ldw + j]
   GemmArgs g{dy, weight, dx, nullptr, m, k, n_out, lddy, ldw, lddx, n_out, 0, 0};
   return dtype == GWEN_F32 ? launch_gemm<float, true, false, false>(g, 1, st)
@@ -298,7 +382,9 @@ extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx
 extern "C" int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int64_t n_out,
                                                       size_t* out) {
   GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
-  *out = static_cast<size_t>(wgrad_splits(m, k, n_out)) * n_out * k * sizeof(float) + 256;
+  int splits = wgrad_splits(m, k, n_out);
+  if (k % 64 == 0 && n_out % 64 == 0 && m >= 256) splits = std::max(splits, linear_tc_wgrad_splits(m, k, n_out));
+  *out = static_cast<size_t>(splits) * n_out * k * sizeof(float) + 256;
   return GWEN_OK;
 }
 
@@ -313,6 +399,18 @@ extern "C" int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, 
   GWEN_CHECK_ARG(m == 0 || (dy && x), "null pointer");
   GWEN_CHECK_ARG(lddy >= n_out && ldx >= k && lddw >= k, "row pitch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_elems = n_out * k;
+  if (dtype == GWEN_BF16 && linear_tc_wgrad_supported(m, k, n_out, lddy, ldx, dy, x)) {
+    const int tsplits = linear_tc_wgrad_splits(m, k, n_out);
+    const size_t tneed = static_cast<size_t>(tsplits) * n_out * k * sizeof(float);
+    if (ws_bytes < tneed) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, tneed);
+    int rc = linear_tc_wgrad_bf16(dy, x, static_cast<float*>(ws), m, k, n_out, lddy, ldx, st);
+    if (rc != GWEN_OK) return rc;
+    k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(
+        static_cast<const float*>(ws), tsplits, n_elems, n_elems, dw, lddw, k);
+    GWEN_LAUNCH_CHECK("k_reduce_splits");
+    return GWEN_OK;
+  }
   const int splits = wgrad_splits(m, k, n_out);
   const size_t need = static_cast<size_t>(splits) * n_out * k * sizeof(float);
   if (ws_bytes < need) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
@@ -323,7 +421,6 @@ extern "C" int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, 
   int rc = dtype == GWEN_F32 ? launch_gemm<float, false, false, true>(g, splits, st)
                              : launch_gemm<__nv_bfloat16, false, false, true>(g, splits, st);
   if (rc != GWEN_OK) return rc;
-  const int64_t n_elems = n_out * k;
   k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(
       static_cast<const float*>(ws), splits, n_elems, n_elems, dw, lddw, k);
   GWEN_LAUNCH_CHECK("k_reduce_splits");
@@ -380,5 +477,40 @@ extern "C" int gwen_bias_grad(const void* dy, float* db, int64_t rows, int64_t f
   k_reduce_splits<<<static_cast<unsigned>(ceil_div(feat, 256)), 256, 0, st>>>(
       part, static_cast<int>(chunks), feat, feat, db, feat, feat);
   GWEN_LAUNCH_CHECK("k_reduce_splits");
+  return GWEN_OK;
+}
+
+extern "C" int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float* db, int64_t rows,
+                                  int64_t feat, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  GWEN_CHECK_ARG(rows >= 0 && feat >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (feat == 0) return GWEN_OK;
+  GWEN_CHECK_ARG((rows == 0 || dy) && (!y || dz) && (!db || ws), "null pointer");
+  const int vn = dtype == GWEN_F32 ? 4 : 8;
+  const int64_t groups = feat / vn;
+  if (feat % vn || groups > 256 || 256 % groups || !aligned16(dy) || !aligned16(y) || !aligned16(dz))
+    return set_err(GWEN_E_NOSUPPORT, "fused relu/bias backward needs feat = %d * (a divisor of 256)", vn);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t chunks = std::max<int64_t>(1, ceil_div(rows, kBiasChunk));
+  if (db) {
+    const size_t need = static_cast<size_t>(chunks) * feat * sizeof(float);
+    if (ws_bytes < need) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
+  }
+  float* part = db ? static_cast<float*>(ws) : nullptr;
+  if (!y && !db) return GWEN_OK;
+  if (dtype == GWEN_F32)
+    k_relu_bias_bwd<float><<<static_cast<unsigned>(chunks), 256, 0, st>>>(
+        static_cast<const float*>(y), static_cast<const float*>(dy), static_cast<float*>(dz), rows,
+        static_cast<int>(groups), kBiasChunk, part);
+  else
+    k_relu_bias_bwd<__nv_bfloat16><<<static_cast<unsigned>(chunks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(dy),
+        static_cast<__nv_bfloat16*>(dz), rows, static_cast<int>(groups), kBiasChunk, part);
+  GWEN_LAUNCH_CHECK("k_relu_bias_bwd");
+  if (db) {
+    k_reduce_splits<<<static_cast<unsigned>(ceil_div(feat, 256)), 256, 0, st>>>(
+        part, static_cast<int>(chunks), feat, feat, db, feat, feat);
+    GWEN_LAUNCH_CHECK("k_reduce_splits");
+  }
   return GWEN_OK;
 }

@@ -26,10 +26,10 @@ namespace gwen {
 using namespace tc;
 
 // linear_tc3.cu (CTA-pair kernel)
-int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out);
+int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn);
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
-                        cudaStream_t st);
+                        int b_mn, cudaStream_t st);
 
 namespace {
 
@@ -377,8 +377,8 @@ int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t
                        int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
                        cudaStream_t st) {
   static const bool v1_only = getenv("GWEN_TC_V1") != nullptr;
-  if (!v1_only && linear_tc3_supported(m, k, n_out))
-    return linear_tc3_fwd_bf16(x, w, y, m, k, n_out, ldx, ldw, ldy, bias, relu, st);
+  if (!v1_only && linear_tc3_supported(m, k, n_out, 0))
+    return linear_tc3_fwd_bf16(x, w, y, m, k, n_out, ldx, ldw, ldy, bias, relu, 0, st);
   if (!v1_only && n_out % 64 == 0)
     return linear_tc2_fwd_bf16(x, w, y, m, k, n_out, ldx, ldw, ldy, bias, relu, st);
   const int bn = pick_bn(n_out);
@@ -404,6 +404,19 @@ int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t
   k_linear_tc<<<static_cast<unsigned>(grid), kTcThreads, smem, st>>>(amap, bmap, g);
   GWEN_LAUNCH_CHECK("k_linear_tc");
   return GWEN_OK;
+}
+
+
+// dx[M, K_in] = dy[M, N_out] W[N_out, K_in]: the forward kernel with the reduction over N_out and
+// W read as an MN-major B operand (no transposed copy of the weights).
+int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldw,
+                              int64_t lddx, const void* dy, const void* w, const void* dx) {
+  if (!linear_tc_supported(m, n_out, k_in, lddy, ldw, lddx, dy, w, dx)) return 0;
+  return linear_tc3_supported(m, n_out, k_in, 1);
+}
+int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
+                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st) {
+  return linear_tc3_fwd_bf16(dy, w, dx, m, n_out, k_in, lddy, ldw, lddx, nullptr, 0, 1, st);
 }
 
 }  // namespace gwen

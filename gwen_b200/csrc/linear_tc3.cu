@@ -44,6 +44,7 @@ struct Tc3Args {
   const float* bias;
   int64_t m;
   int n, k_blocks, bn, stages, relu, bufs, row_major_tiles;
+  int b_mn;  // B operand is MN-major: w is [reduction][n] row-major (dgrad: dx = dy W)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -207,13 +208,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
           const uint32_t dst = base + s * stage_bytes;
           tma_load_3d_pair(dst, &amap, kb * BK, m0, 0, bar);
-          tma_load_3d_pair(dst + a_bytes, &bmap, kb * BK, n0, 0, bar);
+          if (!g.b_mn) {
+            tma_load_3d_pair(dst + a_bytes, &bmap, kb * BK, n0, 0, bar);
+          } else {  // 64 (n) x 64 (reduction) boxes, one per 64 output columns, 8 KB apart
+            for (int i = 0; i < g.bn / 128; ++i)
+              tma_load_3d_pair(dst + a_bytes + uint32_t(i) * 8192u, &bmap, n0 + 64 * i, kb * BK, 0, bar);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {  // ===== MMA issuer (leader CTA) =====
-      const uint32_t idesc = make_idesc_pair(g.bn);
+      const uint32_t idesc = make_idesc_pair(g.bn) | (g.b_mn ? (1u << 16) : 0u);  // bit 16: B MN-major
       uint32_t it = 0, seq = 0;
       for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
         const uint32_t acc = seq & 1u, use = seq >> 1;
@@ -225,10 +231,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           mbar_wait(smem_u32(&full_bar[s]), (it / uint32_t(g.stages)) & 1u);
           tc_fence_after();
           const uint32_t a_addr = base + s * stage_bytes;
-          const uint64_t adesc = make_smem_desc(a_addr), bdesc = make_smem_desc(a_addr + a_bytes);
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = g.b_mn ? make_smem_desc_mn(a_addr + a_bytes, 8192u)
+                                        : make_smem_desc(a_addr + a_bytes);
+          // per UMMA_K = 16: K-major +32 B inside the swizzle row; MN-major +16 rows of 128 B
+          const uint64_t bstep = g.b_mn ? uint64_t(2048 >> 4) : uint64_t(2);
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk)
-            umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
+            umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk) * bstep, idesc,
                           (kb | kk) ? 1u : 0u);
           umma_commit_pair(smem_u32(&empty_bar[s]));
         }
@@ -308,14 +318,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
 
 }  // namespace
 
-int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out) {
+int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn) {
   static const bool disabled = getenv("GWEN_TC_NO_PAIR") != nullptr;
+  if (b_mn && n_out % 128) return 0;  // each CTA of the pair stages whole 64-column boxes
   return !disabled && n_out % 64 == 0 && n_out <= 8192 && m >= 256 && k >= 8 && sm_count() % 2 == 0;
 }
 
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
-                        cudaStream_t st) {
+                        int b_mn, cudaStream_t st) {
   int bn = 0;
   for (int c : {256, 128, 64})
     if (n_out % c == 0) { bn = c; break; }
@@ -323,7 +334,8 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   CUtensorMap amap, bmap, ymap;
   int rc = make_tensor_map_3d(&amap, x, GWEN_BF16, k, m, 1, ldx, 0, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
-  rc = make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = b_mn ? make_tensor_map_3d(&bmap, w, GWEN_BF16, n_out, k, 1, ldw, 0, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B)
+            : make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
   rc = make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, 1, ldy, 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != GWEN_OK) return rc;
@@ -350,7 +362,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   }();
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
-  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major};
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, b_mn};
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);

@@ -1,0 +1,194 @@
+// K2 backward (weight gradient) on the tensor cores:  dW[N_out, K_in] = dY^T X, reduced over the
+// M rows (nodes x members), bf16 operands, fp32 accumulation.
+//
+// Both operands are read exactly as they lie in memory ([M, N_out] and [M, K_in] row-major): the
+// reduction index (the row) is the SLOW index of both, i.e. both are MN-major UMMA operands.  TMA
+// boxes of {64 columns, 64 rows} with SWIZZLE_128B land as the canonical MN-major tile (row r at
+// byte 128 r, 8-row groups 1024 B apart, 64-column chunks one box apart), so no transposed copy of
+// the activations is ever made.
+//
+// CTA (tile, split): one 128 (N_out) x BN (K_in) tile of dW over the rows [split * per, +per):
+//   warp 0 lane 0  TMA producer: per 64-row block two dY boxes + BN/64 X boxes into a 4-stage ring
+//   warp 1 lane 0  4 x tcgen05.mma (M = 128, N = BN, K = 16, A and B MN-major) per block into one
+//                  TMEM accumulator; tcgen05.commit frees the stage / publishes the accumulator
+//   warps 2..5     tcgen05.ld -> fp32 partial tile -> workspace[split] (16-byte stores)
+// The partials are summed in split order by k_reduce_splits (linear.cu): deterministic.
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tma.cuh"
+#include "tcgen05.cuh"
+
+namespace gwen {
+using namespace tc;
+namespace {
+
+constexpr int RK = 64;  // rows (reduction) per stage
+constexpr int kWgThreads = 192;
+
+struct WgArgs {
+  float* part;           // [splits][n_out][k_in]
+  int64_t m, per;        // rows, rows per split (multiple of RK)
+  int n_out, k_in, bn, stages, tiles_j;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+    k_wgrad_tc(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
+               WgArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t box_bytes = RK * 128;                       // one {64 col, RK row} box
+  const uint32_t a_bytes = 2 * box_bytes, b_bytes = uint32_t(g.bn / 64) * box_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int i0 = (tile / g.tiles_j) * BM, j0 = (tile % g.tiles_j) * g.bn;
+  const int64_t r_begin = int64_t(split) * g.per;
+  const int64_t r_end = r_begin + g.per < g.m ? r_begin + g.per : g.m;
+  const int n_blocks = r_end > r_begin ? int((r_end - r_begin + RK - 1) / RK) : 0;
+  const uint32_t tmem_cols = uint32_t(g.bn < 32 ? 32 : g.bn);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&dymap);
+    tma_prefetch_desc(&xmap);
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const int s = blk % g.stages;
+        const uint32_t round = uint32_t(blk / g.stages);
+        if (round > 0) mbar_wait(smem_u32(&empty_bar[s]), (round - 1) & 1u);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t dst = base + uint32_t(s) * stage_bytes;
+        const int r0 = int(r_begin) + blk * RK;   // rows beyond m are zero-filled by TMA
+        mbar_expect_tx(bar, stage_bytes);
+        tma_load_3d(dst, &dymap, i0, r0, 0, bar);
+        tma_load_3d(dst + box_bytes, &dymap, i0 + 64, r0, 0, bar);
+        for (int c = 0; c < g.bn / 64; ++c)
+          tma_load_3d(dst + a_bytes + uint32_t(c) * box_bytes, &xmap, j0 + 64 * c, r0, 0, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      // kind::f16, D fp32, A = B = bf16, both MN-major (bits 15, 16), M = 128, N = bn
+      const uint32_t idesc = make_idesc(g.bn) | (1u << 15) | (1u << 16);
+      for (int blk = 0; blk < n_blocks; ++blk) {
+        const int s = blk % g.stages;
+        mbar_wait(smem_u32(&full_bar[s]), uint32_t(blk / g.stages) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = base + uint32_t(s) * stage_bytes;
+        const uint64_t adesc = make_smem_desc_mn(a_addr, box_bytes);
+        const uint64_t bdesc = make_smem_desc_mn(a_addr + a_bytes, box_bytes);
+#pragma unroll
+        for (int kk = 0; kk < RK / UMMA_K; ++kk)  // 16 rows of 128 B per UMMA_K
+          umma_f16(tmem_d, adesc + uint64_t(kk) * (2048 >> 4), bdesc + uint64_t(kk) * (2048 >> 4),
+                   idesc, (blk | kk) ? 1u : 0u);
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&tmem_full_bar));
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lanes 32 (warp % 4) .. +31 = tile rows =====
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;
+    float* prow = g.part + (int64_t(split) * g.n_out + i) * g.k_in + j0;
+    if (n_blocks > 0) {
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      tc_fence_after();
+    }
+    for (int c = 0; c < g.bn; c += 32) {
+      uint32_t r[32];
+      if (n_blocks > 0) {
+        tmem_ld32(tmem_d + (uint32_t(q * 32) << 16) + uint32_t(c), r);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) r[t] = 0u;
+      }
+      if (i < g.n_out) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 4)
+          *reinterpret_cast<uint4*>(prow + c + t) = make_uint4(r[t], r[t + 1], r[t + 2], r[t + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
+                 "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+int pick_bn_wg(int64_t k_in) {
+  for (int bn : {256, 128, 64})
+    if (k_in % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
+                              const void* dy, const void* x) {
+  static const bool disabled = getenv("GWEN_DISABLE_TC") != nullptr;
+  if (disabled || m < 256 || m > INT32_MAX) return 0;
+  if (k_in % 64 || n_out % 64 || lddy % 8 || ldx % 8 || !aligned16(dy) || !aligned16(x)) return 0;
+  return 1;
+}
+
+// number of row splits (partials) the tensor-core wgrad writes for this problem
+int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out) {
+  const int bn = pick_bn_wg(k_in);
+  const int64_t tiles = ceil_div(n_out, BM) * (k_in / bn);
+  int64_t s = std::max<int64_t>(1, sm_count() / tiles);
+  s = std::min<int64_t>(s, std::max<int64_t>(1, m / (4 * RK)));
+  return static_cast<int>(std::min<int64_t>(s, 65535));
+}
+
+int linear_tc_wgrad_bf16(const void* dy, const void* x, float* part, int64_t m, int64_t k_in,
+                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st) {
+  const int bn = pick_bn_wg(k_in);
+  if (!bn) return set_err(GWEN_E_NOSUPPORT, "tcgen05 wgrad needs k_in %% 64 == 0");
+  CUtensorMap dymap, xmap;
+  int rc = make_tensor_map_3d(&dymap, dy, GWEN_BF16, n_out, m, 1, lddy, 0, 64, RK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  rc = make_tensor_map_3d(&xmap, x, GWEN_BF16, k_in, m, 1, ldx, 0, 64, RK, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != GWEN_OK) return rc;
+  const int splits = linear_tc_wgrad_splits(m, k_in, n_out);
+  const int64_t per = ceil_div(ceil_div(m, splits), RK) * RK;
+  const size_t stage_bytes = size_t(2 + bn / 64) * RK * 128;
+  const int stages = static_cast<int>(std::min<size_t>(8, (224 * 1024) / stage_bytes));
+  const size_t smem = std::max<size_t>(stages * stage_bytes + 1024, 120 * 1024);  // one CTA per SM
+  const int tiles_j = static_cast<int>(k_in / bn);
+  WgArgs g{part, m, per, static_cast<int>(n_out), static_cast<int>(k_in), bn, stages, tiles_j};
+  GWEN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(ceil_div(n_out, BM) * tiles_j), static_cast<unsigned>(splits));
+  k_wgrad_tc<<<grid, kWgThreads, smem, st>>>(dymap, xmap, g);
+  GWEN_LAUNCH_CHECK("k_wgrad_tc");
+  return GWEN_OK;
+}
+
+}  // namespace gwen

@@ -29,6 +29,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= uint64_t(2) << 61;                         // layout type: SWIZZLE_128B
   return d;
 }
+// MN-major operand tile as TMA writes it with SWIZZLE_128B boxes of {64 elements (MN, contiguous
+// in global memory), R rows (K)}: K row r at byte 128 r (chunks XOR-swizzled by r % 8), 8-row K
+// groups 1024 B apart (SBO), successive 64-element MN chunks `lbo_bytes` apart (LBO) -- the
+// canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) layout in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);
+  d |= uint64_t(lbo_bytes >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: D = fp32, A = B = bf16, both K-major, M = 128, N = bn.
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);

@@ -157,6 +157,10 @@ class GraphCSR:
     # -- backward graph ----------------------------------------------------------------------
     def transposed(self) -> "GraphCSR":
         """CSR of the transposed graph with the SAME per-edge weights (Appendix A.7)."""
+        if self._transposed is None and self.is_plain_mesh:
+            # the normalised mesh operator is symmetric (undirected edges, w = dis[s] * dis[d]):
+            # A_hat^T = A_hat, and the stencil fast path serves the backward pass too
+            self._transposed = self
         if self._transposed is None:
             if self.edge_index is None:
                 raise RuntimeError("transposed graph needs the original edge_index")

@@ -48,10 +48,10 @@ class _GCNConvFn(torch.autograd.Function):
     def backward(ctx, dy: Tensor):
         saved_in, weight, y = ctx.saved_tensors
         graph_t = ctx.graph.transposed()
-        dy = dy.contiguous()
-        if ctx.relu:
-            dy = ops.relu_bwd_(y, dy.clone())
-        db = ops.bias_grad(dy).to(weight.dtype) if ctx.has_bias else None
+        # ReLU mask and bias gradient in one pass over dy (out of place: autograd owns dy)
+        dy, db = ops.relu_bias_bwd(dy.contiguous(), y if ctx.relu else None, ctx.has_bias)
+        if db is not None:
+            db = db.to(weight.dtype)
         need_dx = ctx.needs_input_grad[0]
         dx = None
         if ctx.agg_first:

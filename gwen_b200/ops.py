@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
-__all__ = ["aggregate", "mesh_stencil", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad",
+__all__ = ["aggregate", "mesh_stencil", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd",
            "rows_gather", "rows_scatter_", "dtype_code"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
@@ -197,6 +197,37 @@ def bias_grad(dy: torch.Tensor) -> torch.Tensor:
         check(lib().gwen_bias_grad(_ptr(dy2), _ptr(db), dy2.shape[0], f, f, dtype_code(dy2.dtype),
                                    _ptr(ws), need.value, _stream()), "gwen_bias_grad")
     return db
+
+
+def relu_bias_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], want_db: bool):
+    """(dz, db): dz = dy * (y > 0) (dy itself when ``y`` is None) and db = column sums of dz in fp32
+    (None unless ``want_db``), fused in one pass when the width allows, else the two kernels."""
+    f = dy.shape[-1]
+    dy2 = dy.reshape(-1, f)
+    if not dy2.is_contiguous():
+        dy2 = dy2.contiguous()
+    vn = 16 // dy2.element_size()
+    groups = f // vn
+    fused = f % vn == 0 and 0 < groups <= 256 and 256 % groups == 0
+    if y is None and not want_db:
+        return dy, None
+    if not fused:
+        dz = relu_bwd_(y, dy2.clone().reshape(y.shape)) if y is not None else dy
+        return dz, (bias_grad(dz) if want_db else None)
+    y2 = None if y is None else y.reshape(-1, f)
+    assert y2 is None or y2.is_contiguous()
+    with torch.cuda.device(dy2.device):
+        dz = torch.empty_like(dy2) if y2 is not None else dy2
+        db = ws = None
+        need = C.c_size_t(0)
+        if want_db:
+            check(lib().gwen_bias_grad_workspace_bytes(dy2.shape[0], f, C.byref(need)), "bias ws")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device)
+            db = torch.empty(f, dtype=torch.float32, device=dy2.device)
+        check(lib().gwen_relu_bias_bwd(_ptr(y2), _ptr(dy2), _ptr(dz) if y2 is not None else None, _ptr(db),
+                                       dy2.shape[0], f, dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
+              "gwen_relu_bias_bwd")
+    return dz.reshape(dy.shape), db
 
 
 def rows_gather(x: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

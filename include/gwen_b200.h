@@ -262,6 +262,12 @@ int gwen_relu_bwd(const void* y, void* dy, int64_t rows, int64_t feat, int64_t l
 int gwen_bias_grad(const void* dy, float* db, int64_t rows, int64_t feat, int64_t lddy, int dtype,
                    void* ws, size_t ws_bytes, void* stream);
 int gwen_bias_grad_workspace_bytes(int64_t rows, int64_t feat, size_t* bytes_out_host);
+/* Both in one pass over contiguous [rows, feat] tensors: dz = dy * (y > 0) (skipped when y is
+ * NULL; dz may alias dy) and db[f] = sum_rows dz[:, f] (skipped when db is NULL; workspace as for
+ * gwen_bias_grad).  Needs feat = (16 / element size) * d with d a divisor of 256, else
+ * GWEN_E_NOSUPPORT (use the two calls above). */
+int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float* db, int64_t rows,
+                       int64_t feat, int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Halo exchange helpers for the row-band mesh partition (no reference counterpart; SURVEY.md

@@ -284,6 +284,35 @@ def test_linear_backward_pieces(dev, m, k, n):
     y = wts.features((m, n), 4)
     d2 = ops.relu_bwd_(y.to(dev), dy.to(dev).clone())
     assert torch.equal(d2.cpu(), dy * (y > 0))
+    # fused mask + bias gradient (one pass when the width allows, the two kernels otherwise)
+    dz, db2 = ops.relu_bias_bwd(dy.to(dev), y.to(dev), True)
+    assert torch.equal(dz.cpu(), dy * (y > 0))
+    assert nmax(db2, (dy * (y > 0)).double().sum(0)) <= FP32_TOL
+    dz0, db0 = ops.relu_bias_bwd(dy.to(dev), None, True)
+    assert torch.equal(dz0.cpu(), dy) and nmax(db0, dy.double().sum(0)) <= FP32_TOL
+    yb, dyb = y.bfloat16(), dy.bfloat16()
+    dzb, dbb = ops.relu_bias_bwd(dyb.to(dev), yb.to(dev), True)
+    assert torch.equal(dzb.cpu(), dyb * (yb > 0))
+    assert nmax(dbb, (dyb * (yb > 0)).double().sum(0)) <= FP32_TOL
+    assert torch.equal(dbb, ops.relu_bias_bwd(dyb.to(dev), yb.to(dev), True)[1])   # deterministic
+
+
+@pytest.mark.parametrize("m,k,n", [(1000, 512, 1024), (40000, 256, 192), (300, 1024, 64), (70001, 128, 512),
+                                   (5000, 64, 1024), (257, 96, 40)])
+def test_linear_backward_pieces_bf16(dev, m, k, n):
+    """bf16 dgrad / wgrad (tcgen05 kernels with MN-major operands where the shapes allow, CUDA-core
+    path otherwise) against fp64 references of the same bf16-rounded operands."""
+    x, w, dy = wts.features((m, k), 1).bfloat16(), wts.glorot(n, k, 2).bfloat16(), wts.features((m, n), 3).bfloat16()
+    dx = ops.linear_bwd_data(dy.to(dev), w.to(dev))
+    ref = dy.double() @ w.double()
+    assert dx.dtype == torch.bfloat16
+    err = (dx.double().cpu() - ref).abs()
+    assert torch.all(err <= ref.abs() * 2.0 ** -7 + 1e-3 * ref.abs().max())
+    dw = ops.linear_bwd_weight(dy.to(dev), x.to(dev))
+    refw = dy.double().t() @ x.double()
+    assert dw.dtype == torch.float32
+    assert nmax(dw, refw) <= 1e-5                                           # fp32 accumulation of exact products
+    assert torch.equal(dw, ops.linear_bwd_weight(dy.to(dev), x.to(dev)))   # deterministic
 
 
 # ---------------------------------------------------------------------------------------------
