@@ -32,6 +32,36 @@ namespace {
 constexpr int TH = 8;     // destination rows per tile
 constexpr int SEG = 8;    // destination columns a sub-warp walks per unit
 
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE fp32 lanes per instruction,
+// each rounded exactly like the scalar op).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 template <typename T>
 struct V16;
 template <>
@@ -44,6 +74,21 @@ struct V16<float> {
   __device__ static uint4 pack(const float* f) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
                       __float_as_uint(f[3]));
+  }
+  // 16 bytes <-> N/2 packed fp32 pairs
+  __device__ static void unpack2(const uint4& r, uint64_t* p) {
+    p[0] = pk2u(r.x, r.y);
+    p[1] = pk2u(r.z, r.w);
+  }
+  __device__ static uint4 pack2(const uint64_t* p, bool relu) {
+    float f[4];
+    unpk2(p[0], f[0], f[1]);
+    unpk2(p[1], f[2], f[3]);
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    return pack(f);
   }
 };
 template <>
@@ -63,6 +108,23 @@ struct V16<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) {
       __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
       u[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    return make_uint4(u[0], u[1], u[2], u[3]);
+  }
+  __device__ static void unpack2(const uint4& r, uint64_t* p) {
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = pk2u(u[i] << 16, u[i] & 0xffff0000u);
+  }
+  __device__ static uint4 pack2(const uint64_t* p, bool relu) {
+    uint32_t u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float lo, hi;
+      unpk2(p[i], lo, hi);
+      __nv_bfloat162 q = __floats2bfloat162_rn(lo, hi);
+      u[i] = *reinterpret_cast<uint32_t*>(&q);
+      if (relu) asm("max.bf16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(0u));  // clamp after rounding == before
     }
     return make_uint4(u[0], u[1], u[2], u[3]);
   }
@@ -175,8 +237,8 @@ __global__ void __launch_bounds__(576, 1)
   const int my_tiles = a.num_tiles > int(blockIdx.x)
                            ? (a.num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
   const int64_t n_items = int64_t(my_tiles) * per_tile;
-  const uint32_t slab_bytes = a.slab_elems * sizeof(T);
-  const uint32_t srow_bytes = uint32_t(a.tw + 2) * slab_bytes;  // one staged mesh row
+  constexpr uint32_t kSlabBytes = LPR * 16u;                     // = a.slab_elems * sizeof(T)
+  const uint32_t srow_bytes = uint32_t(a.tw + 2) * kSlabBytes;  // one staged mesh row
 
   // Peer mode walks the interior tile rows first and the two tile rows that read a halo row last
   // (tile row 0, then the bottom one), so the halo fetch runs under the interior work.
@@ -275,50 +337,58 @@ __global__ void __launch_bounds__(576, 1)
     const bool on = col < a.feat;
     const uint32_t xs = stage0 + uint32_t(st) * a.stage_bytes;
     const uint32_t ds = xs + a.x_bytes;
-    float bv[VN];
+    constexpr int VP = VN / 2;  // packed fp32 pairs per 16 bytes
+    uint64_t bv[VP];
 #pragma unroll
-    for (int k = 0; k < VN; ++k) bv[k] = (a.bias && on) ? __ldg(a.bias + col + k) : 0.0f;
+    for (int k = 0; k < VP; ++k)
+      bv[k] = (a.bias && on) ? pk2(__ldg(a.bias + col + 2 * k), __ldg(a.bias + col + 2 * k + 1)) : 0ull;
     T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
+    const bool relu = a.relu != 0;
     mbar_wait(smem_u32(&full_bar[st]), round & 1u);
-    for (int u = warp * RPW + sub; u < units; u += ncw * RPW) {
-      const int r = u / nseg, cb = (u % nseg) * SEG;
-      if (r >= rows_valid || cb >= cols_valid) continue;
-      // staged rows r, r+1, r+2 hold mesh rows (r0+r-1 .. r0+r+1); staged column t = mesh c0-1+t
-      const uint32_t xrow = xs + uint32_t(r) * srow_bytes + uint32_t(cb) * slab_bytes + uint32_t(l) * 16u;
-      const uint32_t drow = ds + uint32_t(r) * a.dis_pitch + uint32_t(cb) * 4u;
-      float s0[VN], s1[VN], s2[VN];  // column sums of staged columns t-2, t-1, t
-      float dmid_prev = 0.0f;        // dis of the destination under the window centre
+    if (on) {
+      for (int u = warp * RPW + sub; u < units; u += ncw * RPW) {
+        const int r = u / nseg, cb = (u - r * nseg) * SEG;
+        const int nvalid = cols_valid - cb;  // destinations of this unit inside the mesh
+        if (r >= rows_valid || nvalid <= 0) continue;
+        // staged rows r, r+1, r+2 hold mesh rows (r0+r-1 .. r0+r+1); staged column t = mesh c0-1+t
+        const uint32_t x0 = xs + uint32_t(r) * srow_bytes + uint32_t(cb) * kSlabBytes + uint32_t(l) * 16u;
+        const uint32_t x1 = x0 + srow_bytes, x2 = x1 + srow_bytes;
+        const uint32_t q0 = ds + uint32_t(r) * a.dis_pitch + uint32_t(cb) * 4u;
+        const uint32_t q1 = q0 + a.dis_pitch, q2 = q1 + a.dis_pitch;
+        T* op = ob + (int64_t(r0 + r) * a.w + (c0 + cb)) * a.ldo;  // destination column cb
+        uint64_t s0[VP], s1[VP], s2[VP];  // column sums of staged columns t-2, t-1, t
+        float dmid_prev = 0.0f;           // dis of the destination under the window centre
 #pragma unroll
-      for (int tt = 0; tt < SEG + 2; ++tt) {
-        const uint4 v0 = lds128(xrow + uint32_t(tt) * slab_bytes);
-        const uint4 v1 = lds128(xrow + srow_bytes + uint32_t(tt) * slab_bytes);
-        const uint4 v2 = lds128(xrow + 2 * srow_bytes + uint32_t(tt) * slab_bytes);
-        const float d0 = lds32(drow + uint32_t(tt) * 4u);
-        const float d1 = lds32(drow + a.dis_pitch + uint32_t(tt) * 4u);
-        const float d2 = lds32(drow + 2 * a.dis_pitch + uint32_t(tt) * 4u);
-        float f0[VN], f1[VN], f2[VN];
-        V16<T>::unpack(v0, f0);
-        V16<T>::unpack(v1, f1);
-        V16<T>::unpack(v2, f2);
+        for (int tt = 0; tt < SEG + 2; ++tt) {
+          const uint4 v0 = lds128(x0 + uint32_t(tt) * kSlabBytes);
+          const uint4 v1 = lds128(x1 + uint32_t(tt) * kSlabBytes);
+          const uint4 v2 = lds128(x2 + uint32_t(tt) * kSlabBytes);
+          const float d0 = lds32(q0 + uint32_t(tt) * 4u);
+          const float d1 = lds32(q1 + uint32_t(tt) * 4u);
+          const float d2 = lds32(q2 + uint32_t(tt) * 4u);
+          uint64_t f0[VP], f1[VP], f2[VP];
+          V16<T>::unpack2(v0, f0);
+          V16<T>::unpack2(v1, f1);
+          V16<T>::unpack2(v2, f2);
+          const uint64_t e0 = pk2(d0, d0), e1 = pk2(d1, d1), e2 = pk2(d2, d2);
 #pragma unroll
-        for (int k = 0; k < VN; ++k) {
-          s0[k] = s1[k];
-          s1[k] = s2[k];
-          s2[k] = fmaf(d2, f2[k], fmaf(d1, f1[k], d0 * f0[k]));
-        }
-        if (tt >= 2) {  // destination column j = cb + tt - 2 (window = staged columns tt-2 .. tt)
-          const int j = cb + tt - 2;
-          if (j < cols_valid && on) {
-            float o[VN];
-#pragma unroll
-            for (int k = 0; k < VN; ++k) {
-              o[k] = dmid_prev * ((s0[k] + s1[k]) + s2[k]) + bv[k];
-              if (a.relu) o[k] = fmaxf(o[k], 0.0f);
-            }
-            stg128(ob + (int64_t(r0 + r) * a.w + (c0 + j)) * a.ldo, V16<T>::pack(o));
+          for (int k = 0; k < VP; ++k) {
+            s0[k] = s1[k];
+            s1[k] = s2[k];
+            s2[k] = fma2(e2, f2[k], fma2(e1, f1[k], mul2(e0, f0[k])));
           }
+          if (tt >= 2) {  // destination column cb + tt - 2 (window = staged columns tt-2 .. tt)
+            if (tt - 2 < nvalid) {
+              const uint64_t dm = pk2(dmid_prev, dmid_prev);
+              uint64_t o[VP];
+#pragma unroll
+              for (int k = 0; k < VP; ++k) o[k] = fma2(dm, add2(add2(s0[k], s1[k]), s2[k]), bv[k]);
+              stg128(op, V16<T>::pack2(o, relu));
+            }
+            op += a.ldo;
+          }
+          dmid_prev = d1;  // dis of mesh node (r0+r, c0-1+tt): the centre of the NEXT window
         }
-        dmid_prev = d1;  // dis of mesh node (r0+r, c0-1+tt): the centre of the NEXT window
       }
     }
     __syncwarp();
@@ -384,9 +454,11 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
   if (feat % vn || ldx % vn || ldo % vn || x_bstride % vn || o_bstride % vn || !aligned16(x) ||
       !aligned16(out))
     return set_err(GWEN_E_ALIGN, "grid stencil needs 16-byte aligned rows (feat %% %d == 0)", vn);
-  int tw = tile_w > 0 ? tile_w : 32;
+  // defaults from the cfg 2 / cfg 3 sweeps (tools/sweep_agg.py): fp32 16-wide tiles with 64-float
+  // slabs (4 stages of 46 KB), bf16 32-wide tiles with 256-element slabs
+  int tw = tile_w > 0 ? tile_w : (dtype == GWEN_F32 ? 16 : 32);
   GWEN_CHECK_ARG(tw % SEG == 0 && tw >= SEG && tw <= 128, "tile_w must be a multiple of %d", SEG);
-  int lpr = slab_elems > 0 ? static_cast<int>(slab_elems / vn) : 16;
+  int lpr = slab_elems > 0 ? static_cast<int>(slab_elems / vn) : (dtype == GWEN_F32 ? 16 : 32);
   if (lpr != 8 && lpr != 16 && lpr != 32)
     return set_err(GWEN_E_BADARG, "slab_elems must be %d, %d or %d", 8 * vn, 16 * vn, 32 * vn);
   while (lpr > 8 && lpr * vn / 2 >= feat) lpr /= 2;
@@ -399,7 +471,7 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
   while (lpr > 8 && 2 * stage_for(lpr) + 256 > smem_cap) lpr /= 2;
   if (2 * stage_for(lpr) + 256 > smem_cap)
     return set_err(GWEN_E_NOSUPPORT, "stencil tile does not fit in shared memory");
-  static const int stage_hint = env_int2("GWEN_STENCIL_STAGES", 3, 2, 8);
+  static const int stage_hint = env_int2("GWEN_STENCIL_STAGES", 4, 2, 8);
   int ns = 2;
   while (ns < stage_hint && (ns + 1) * stage_for(lpr) + 256 <= smem_cap) ++ns;
   const int slab = lpr * vn;
