@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model-probes", action="store_true",
+                    help="skip the cfg3 full-forward / cfg5 member-step context numbers (N = 1)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange inside the kernel over peer memory, or NCCL send/recv")
     return ap.parse_args()
@@ -161,6 +163,64 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+# ---------------------------------------------------------------------------------------------
+# context numbers for the other BASELINE configs (N = 1 only, a few seconds): the full six-layer
+# GNNModel forward at config 3 and one forward+backward member step at the config 5 shape
+# ---------------------------------------------------------------------------------------------
+def model_probes(dev):
+    import torch
+    import gwen_b200 as gw
+    h, wd, c, b = 1158, 774, 64, 8
+    n = h * wd
+    out = {}
+    torch.manual_seed(23)
+    ei = gw.grid(h, wd, dev)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
+    model = gw.GNNModel(cfg).to(dev).to(torch.bfloat16)
+    x = torch.randn(b, n, c, device=dev).to(torch.bfloat16)
+
+    def timed(fn, warm, iters):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    with torch.no_grad():
+        ms = timed(lambda: model(x, ei), 2, 5)
+    e1 = gw.grid_edge_count(h, wd)
+    out["full_forward_cfg3"] = {
+        "workload": "cfg3: COSMO-1E grid 1158x774 (896292 nodes, E'=%d), six GCN layers 64-1024-512-256-512-1024-64, bf16, "
+                    "8 ensemble members per step, synthetic data, random-init weights" % e1,
+        "ms_per_step": ms, "grid_steps_per_s": 1e3 / ms, "member_steps_per_s": b * 1e3 / ms,
+        "edges_per_s": b * e1 * 6 / (ms * 1e-3),
+        "flops_per_step": 2.0 * b * n * 1441792, "tflops": 2.0 * b * n * 1441792 / (ms * 1e-3) / 1e12}
+    del x
+    x1 = torch.randn(1, n, c, device=dev).to(torch.bfloat16)
+    mask = (torch.arange(n, device=dev) % 125) == 124
+
+    def train_step():
+        for p in model.parameters():
+            p.grad = None
+        y = model(x1, ei)
+        gw.loss_func(y[0].float(), x1[0].float(), mask).backward()
+
+    ms_t = timed(train_step, 2, 3)
+    out["train_step_cfg5_member"] = {
+        "workload": "cfg5 shape, one member: forward + masked-L1 loss (target = input, mask id%125==124) + backward "
+                    "through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16, optimizer step excluded",
+        "ms_per_member_step": ms_t, "member_steps_per_s": 1e3 / ms_t}
+    gw.clear_graph_cache()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -362,6 +422,13 @@ def run_ours(args):
                          "us_per_launch": k_us, "algorithmic_bytes_per_launch": alg_bytes,
                          "traffic": ncu_traffic()},
         }
+        if world == 1 and not args.no_model_probes:
+            try:
+                del x, out
+                torch.cuda.empty_cache()
+                line["other_configs"] = model_probes(dev)
+            except Exception as e:  # noqa: BLE001  (context only: never fail the headline line)
+                line["other_configs"] = {"error": str(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             rate, per_step, edges, cores = cpu_propagate_rate(H, 3, warmup=1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
