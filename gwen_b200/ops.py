@@ -124,19 +124,56 @@ def mesh_stencil(x: torch.Tensor, dis_bordered: torch.Tensor, hs: int, hd: int, 
     return out
 
 
+def _rows_view(t: torch.Tensor):
+    """(pointer-compatible [B, rows, F] view, B, rows) of a tensor whose last two dims are a dense
+    row block (row pitch F) and whose leading dims collapse to one batch stride; None if not."""
+    if t.dim() < 2 or t.stride(-1) != 1 or t.stride(-2) != t.shape[-1]:
+        return None
+    if t.dim() == 2:
+        return t.unsqueeze(0)
+    if t.dim() == 3:
+        return t
+    lead = t.shape[:-2]
+    try:
+        return t.view((-1,) + tuple(t.shape[-2:]))
+    except RuntimeError:
+        return None
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-           relu: bool = False) -> torch.Tensor:
-    """y = epi(x @ weight.T + bias); x [..., K], weight [N_out, K]."""
+           relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epi(x @ weight.T + bias); x [..., K], weight [N_out, K].  ``out`` ([..., N_out], rows dense,
+    any batch stride -- e.g. the owned rows of a band buffer) receives the result in place: one launch
+    per batch slice when x or out is batch-strided."""
     _require_cuda(x, "x")
     _require_cuda(weight, "weight")
     k = x.shape[-1]
     n_out = weight.shape[0]
     if weight.shape[1] != k:
         raise ValueError("weight is %s, x has %d features" % (tuple(weight.shape), k))
-    x2 = x.reshape(-1, k).contiguous()
-    wt = weight.detach().to(x2.dtype).contiguous()
-    code = dtype_code(x2.dtype)
+    wt = weight.detach().to(x.dtype).contiguous()
+    code = dtype_code(x.dtype)
     bias32 = _bias32(bias)
+    if out is not None or not x.is_contiguous():
+        xv = _rows_view(x)
+        if xv is None:
+            xv = _rows_view(x.contiguous())
+        if out is None:
+            out = torch.empty(tuple(x.shape[:-1]) + (n_out,), dtype=x.dtype, device=x.device)
+        ov = _rows_view(out)
+        if ov is None or ov.shape[:2] != xv.shape[:2] or ov.shape[2] != n_out or out.dtype != x.dtype:
+            raise ValueError("out must be [..., N_out] with dense rows matching x")
+        with torch.cuda.device(x.device):
+            if xv.shape[0] == 1 or (xv.stride(0) == xv.shape[1] * k and ov.stride(0) == ov.shape[1] * n_out):
+                slices = [(xv, ov, xv.shape[0] * xv.shape[1])]
+            else:
+                slices = [(xv[b], ov[b], xv.shape[1]) for b in range(xv.shape[0])]
+            for xs, os_, m in slices:
+                check(lib().gwen_linear_fwd(_ptr(xs), _ptr(wt), _ptr(os_), m, k, n_out, k, k, n_out, code,
+                                            _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
+                      "gwen_linear_fwd")
+        return out
+    x2 = x.reshape(-1, k).contiguous()
     with torch.cuda.device(x2.device):
         y = torch.empty((x2.shape[0], n_out), dtype=x2.dtype, device=x2.device)
         check(lib().gwen_linear_fwd(_ptr(x2), _ptr(wt), _ptr(y), x2.shape[0], k, n_out, k, k, n_out,
@@ -145,9 +182,19 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return y.reshape(tuple(x.shape[:-1]) + (n_out,))
 
 
-def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """dx = dy @ weight; dy [..., N_out], weight [N_out, K]."""
+def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dy @ weight; dy [..., N_out], weight [N_out, K].  ``out`` as in :func:`linear`."""
     n_out, k = weight.shape
+    if out is not None:
+        dv, ov = _rows_view(dy if dy.is_contiguous() else dy.contiguous()), _rows_view(out)
+        if ov is None or ov.shape[:2] != dv.shape[:2] or ov.shape[2] != k or out.dtype != dy.dtype:
+            raise ValueError("out must be [..., K] with dense rows matching dy")
+        wt = weight.detach().to(dy.dtype).contiguous()
+        with torch.cuda.device(dy.device):
+            for b in range(dv.shape[0]):
+                check(lib().gwen_linear_bwd_data(_ptr(dv[b]), _ptr(wt), _ptr(ov[b]), dv.shape[1], k, n_out, n_out,
+                                                 k, k, dtype_code(dy.dtype), _stream()), "gwen_linear_bwd_data")
+        return out
     dy2 = dy.reshape(-1, n_out).contiguous()
     wt = weight.detach().to(dy2.dtype).contiguous()
     with torch.cuda.device(dy2.device):
@@ -215,7 +262,8 @@ def relu_bias_bwd(dy: torch.Tensor, y: Optional[torch.Tensor], want_db: bool):
         dz = relu_bwd_(y, dy2.clone().reshape(y.shape)) if y is not None else dy
         return dz, (bias_grad(dz) if want_db else None)
     y2 = None if y is None else y.reshape(-1, f)
-    assert y2 is None or y2.is_contiguous()
+    if y2 is not None and not y2.is_contiguous():
+        y2 = y2.contiguous()
     with torch.cuda.device(dy2.device):
         dz = torch.empty_like(dy2) if y2 is not None else dy2
         db = ws = None

@@ -26,7 +26,7 @@ from . import ops
 from .graph import GraphCSR, bordered_dis
 
 __all__ = ["band_ranges", "partition_graph", "HaloExchange", "LocalGraph", "BandAggregator", "MeshBand",
-           "PeerMeshBand"]
+           "PeerMeshBand", "BandGNNModel"]
 
 
 def band_ranges(height: int, width: int, world_size: int) -> List[range]:
@@ -381,3 +381,113 @@ class PeerMeshBand(MeshBand):
                 None if bias32 is None else bias32.data_ptr(), _lib.EPI_RELU if relu else 0, 0, 0,
                 C.byref(peers), torch.cuda.current_stream().cuda_stream), "gwen_grid_stencil_peer_fwd")
         return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the six-layer model on a row band (forward + backward), SURVEY.md section 8(e)
+# ---------------------------------------------------------------------------------------------
+class _BandGCNFn(torch.autograd.Function):
+    """One GCN layer on this rank's band: ``_GCNConvFn`` with the aggregation done by the band
+    (halo exchange inside the kernel).  The tensor that gets aggregated lives in a symmetric buffer
+    of ``net``; producers write into it in place where they can.  Backward: ``A_hat^T = A_hat`` on the
+    mesh, so the gradient aggregation is the same exchange + stencil on gradient buffers."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, net, li, relu, agg_first):
+        band = net.band
+        b = x.shape[0]
+        if agg_first:      # (A_hat x) W^T
+            xs = net.stage(("f", li), x)
+            h = band.aggregate(xs)[:, :band.n_own]
+            y = ops.linear(h, weight, bias, relu, out=net.out_view(li, b, weight.shape[0], x.dtype))
+            saved_in = h
+        else:              # A_hat (x W^T)
+            hs = net.buffer(("f", li), b, weight.shape[0], x.dtype)
+            ops.linear(x, weight, out=band.owned(hs))
+            y = band.aggregate(hs, bias, relu, out=net.out_view(li, b, weight.shape[0], x.dtype))
+            saved_in = x
+        ctx.net, ctx.li, ctx.relu, ctx.agg_first, ctx.has_bias = net, li, relu, agg_first, bias is not None
+        ctx.save_for_backward(saved_in, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved_in, weight, y = ctx.saved_tensors
+        net, li, band = ctx.net, ctx.li, ctx.net.band
+        dz, db = ops.relu_bias_bwd(dy.contiguous(), y if ctx.relu else None, ctx.has_bias)
+        if db is not None:
+            db = db.to(weight.dtype)
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        b = dz.shape[0]
+        if ctx.agg_first:
+            dw = ops.linear_bwd_weight(dz, saved_in)                  # dW = dz^T (A_hat x)
+            if need_dx:
+                gs = net.buffer(("b", li), b, weight.shape[1], dz.dtype)
+                ops.linear_bwd_data(dz, weight, out=band.owned(gs))
+                dx = band.aggregate(gs)
+        else:
+            gs = net.stage(("b", li), dz)
+            dh = band.aggregate(gs)                                   # A_hat^T dz
+            dw = ops.linear_bwd_weight(dh, saved_in)                  # dW = dh^T x
+            if need_dx:
+                dx = ops.linear_bwd_data(dh, weight)
+        return dx, dw.to(weight.dtype), db, None, None, None, None
+
+
+class BandGNNModel(torch.nn.Module):
+    """:class:`gwen_b200.models_gnn.GNNModel` evaluated on one row band per rank (mesh partitioned
+    over the GPUs, ensemble members in the outer batch).  Shares the wrapped model's parameters, so
+    ``state_dict`` and optimizers are the plain model's.  ``forward(x_own [B, n_own, C]) -> [B, n_own, C]``;
+    after ``backward`` call :meth:`allreduce_grads` (the weight / bias gradients of the ranks are partial
+    sums over their own rows).  Outputs are bitwise equal to the un-partitioned model's rows."""
+
+    def __init__(self, model, band: "PeerMeshBand"):
+        super().__init__()
+        self.model, self.band = model, band
+        d, u = model.conv_layers.down_conv_layers, model.conv_layers.up_conv_layers
+        self.layers = [(d.conv1, True), (d.conv2, True), (d.conv3, True),
+                       (u.upconv3, True), (u.upconv4, True), (u.upconv5, False)]
+        self._agg_first = [c.in_channels < c.out_channels for c, _ in self.layers]
+        self._sym = {}
+
+    # -- symmetric staging buffers (allocated collectively, in first-use order, once) -------------
+    def buffer(self, key, batch, feat, dtype) -> torch.Tensor:
+        k = (key, batch, feat, dtype)
+        if k not in self._sym:
+            self._sym[k] = self.band.alloc(batch, feat, dtype, self.band.dis.device)
+        return self._sym[k]
+
+    def stage(self, key, x: torch.Tensor) -> torch.Tensor:
+        """The symmetric buffer for ``key`` holding ``x`` in its owned rows (no copy when the producer
+        already wrote there through :meth:`out_view`)."""
+        t = self.buffer(key, x.shape[0], x.shape[-1], x.dtype)
+        own = self.band.owned(t)
+        if not (x.data_ptr() == own.data_ptr() and x.stride() == own.stride()):
+            own.copy_(x)
+        return t
+
+    def out_view(self, li: int, batch: int, feat: int, dtype):
+        """Where layer ``li`` should write its output: the owned rows of the next layer's staging
+        buffer when that layer aggregates first, else None (a fresh tensor)."""
+        if li + 1 < len(self.layers) and self._agg_first[li + 1]:
+            return self.band.owned(self.buffer(("f", li + 1), batch, feat, dtype))
+        return None
+
+    def forward(self, x_own: torch.Tensor) -> torch.Tensor:
+        x = x_own if x_own.dim() == 3 else x_own.unsqueeze(0)
+        for li, (conv, relu) in enumerate(self.layers):
+            x = _BandGCNFn.apply(x, conv.lin.weight, conv.bias, self, li, relu, self._agg_first[li])
+        return x if x_own.dim() == 3 else x[0]
+
+    def allreduce_grads(self) -> None:
+        """Sum the parameter gradients over the ranks (one flat NCCL all-reduce)."""
+        grads = [p.grad for p in self.model.parameters() if p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1).float() for g in grads])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.band.group)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()

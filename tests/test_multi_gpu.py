@@ -25,3 +25,19 @@ def test_peer_halo_stencil_two_gpus():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["bitwise_equal_to_single_gpu"] is True
+
+
+@pytest.mark.gpu
+def test_band_model_two_gpus():
+    """BandGNNModel (six layers on a row band per rank, in-kernel halo exchange in forward and
+    backward, all-reduced weight gradients) == the un-partitioned model: forward bitwise, grads 1e-4."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29900 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "band_model_check.py"), "--no-time"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4
