@@ -11,8 +11,9 @@ from .nn import GCNConv, gcn_conv
 from .models_gnn import (DownConvLayers, GCNConvLayers, GNNConfig, GNNModel, UpConvLayers,
                          loss_func)
 from . import ops  # noqa: F401
+from .host_stream import HostPropagator
 
 __version__ = "0.1.0"
 __all__ = ["GCNConv", "gcn_conv", "GraphCSR", "build_graph", "get_graph", "clear_graph_cache",
-           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "GNNConfig",
+           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "GNNConfig",
            "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops"]

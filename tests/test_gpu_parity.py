@@ -587,3 +587,25 @@ def test_mesh_band_stencil_equals_single_gpu(dev, world):
         ops.mesh_stencil(xl, band.dis, rows + 2, 1, w, 1, bias=b, relu=True, out=out2[:, :w])
         ops.mesh_stencil(xl, band.dis, rows + 2, 1, w, rows, bias=b, relu=True, out=out2[:, (rows - 1) * w:])
         assert torch.equal(out2, want)
+
+
+@pytest.mark.parametrize("chunks", [1, 5, 64])
+def test_host_propagator_matches_device_path(dev, chunks):
+    """Chunked H2D -> stencil -> D2H pipeline on pinned host tensors == the device-resident
+    aggregation, bitwise, over consecutive calls (double-buffered device sets)."""
+    h, w, f = 37, 29, 64
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    hp = gw.HostPropagator(g, f, torch.float32, chunks=chunks)
+    b = wts.small_bias(f, 3).to(dev)
+    outs, refs = [], []
+    for i in range(3):
+        xh = wts.features((h * w, f), 20 + i).pin_memory()
+        oh = torch.empty(h * w, f).pin_memory()
+        hp(xh, oh, b, relu=True)
+        outs.append(oh)
+        refs.append(ops.aggregate(g, xh.to(dev), b, relu=True, kernel="stencil"))
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r.cpu())
+    with pytest.raises(RuntimeError):
+        hp(torch.empty(h * w, f), outs[0])          # not pinned
