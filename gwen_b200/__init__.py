@@ -12,8 +12,9 @@ from .models_gnn import (DownConvLayers, GCNConvLayers, GNNConfig, GNNModel, UpC
                          loss_func)
 from . import ops  # noqa: F401
 from .host_stream import HostPropagator
+from .train import masked_l1_loss, train_step
 
 __version__ = "0.1.0"
 __all__ = ["GCNConv", "gcn_conv", "GraphCSR", "build_graph", "get_graph", "clear_graph_cache",
-           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "GNNConfig",
+           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "masked_l1_loss", "train_step", "GNNConfig",
            "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops"]

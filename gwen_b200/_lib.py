@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
@@ -105,6 +105,9 @@ PROTOTYPES = {
     "gwen_bias_grad": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _sz, _p]),
     "gwen_bias_grad_workspace_bytes": (_int, [_i64, _i64, C.POINTER(_sz)]),
     "gwen_relu_bias_bwd": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _p, _sz, _p]),
+    "gwen_masked_l1_workspace_bytes": (_int, [_i64, C.POINTER(_sz)]),
+    "gwen_masked_l1_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "gwen_masked_l1_bwd": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p]),
     "gwen_rows_gather": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_rows_scatter": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
 }

@@ -1,0 +1,155 @@
+// Caller-side loss of the reference training loop (src/gwen/models_gnn.py:261-265, used at :370):
+//   loss_func(output, target, mask) = L1Loss()(output[mask], target[mask])
+//                                   = sum_{b, n: mask[n], c} |output - target| / (B * count(mask) * C)
+// The reference's boolean-mask indexing launches nonzero + two gathers and synchronises the host
+// (the size of output[mask] is data dependent).  Here: one pass for the value (per-block partial
+// sums in a fixed order, then a fixed-order final sum -> deterministic), one pass for the gradient
+// dL/doutput = sign(output - target) * mask * dloss / (B * count * C); no host synchronisation, so the
+// training step can be enqueued (or graph-captured) without a round trip.
+#include "common.cuh"
+
+namespace gwen {
+namespace {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossRows = 64;  // node rows per block
+
+// part[blk] = {sum |y - t| over masked rows of this block, number of masked rows}
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) k_l1_partial(const T* __restrict__ y,
+                                                             const T* __restrict__ t,
+                                                             const uint8_t* __restrict__ mask,
+                                                             int64_t batch, int64_t n, int64_t feat,
+                                                             float2* __restrict__ part) {
+  __shared__ float s_sum[kLossThreads];
+  __shared__ int s_cnt[kLossThreads];
+  const int64_t r0 = int64_t(blockIdx.x) * kLossRows, r1 = min(n, r0 + kLossRows);
+  float acc = 0.0f;
+  int cnt = 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    if (!mask[r]) continue;
+    if (threadIdx.x == 0) ++cnt;
+    for (int64_t b = 0; b < batch; ++b) {
+      const T* yr = y + (b * n + r) * feat;
+      const T* tr = t + (b * n + r) * feat;
+      for (int64_t c = threadIdx.x; c < feat; c += kLossThreads)
+        acc += fabsf(to_f32(yr[c]) - to_f32(tr[c]));
+    }
+  }
+  s_sum[threadIdx.x] = acc;
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int s = kLossThreads / 2; s > 0; s >>= 1) {  // fixed tree
+    if (threadIdx.x < s) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = make_float2(s_sum[0], float(s_cnt[0]));
+}
+
+// out[0] = loss, out[1] = 1 / (B * count * C) (the scale the backward pass uses)
+__global__ void __launch_bounds__(kLossThreads) k_l1_final(const float2* __restrict__ part, int blocks,
+                                                           int64_t batch, int64_t feat,
+                                                           float* __restrict__ out) {
+  __shared__ double s_sum[kLossThreads], s_cnt[kLossThreads];
+  double a = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < blocks; i += kLossThreads) {
+    a += part[i].x;
+    c += part[i].y;
+  }
+  s_sum[threadIdx.x] = a;
+  s_cnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int s = kLossThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + s];
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double denom = double(batch) * s_cnt[0] * double(feat);
+    out[0] = float(s_sum[0] / denom);   // 0 / 0 = NaN for an empty mask, like mean() of an empty tensor
+    out[1] = float(1.0 / denom);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLossThreads) k_l1_bwd(const T* __restrict__ y, const T* __restrict__ t,
+                                                         const uint8_t* __restrict__ mask,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ dloss, int64_t batch,
+                                                         int64_t n, int64_t feat, T* __restrict__ dy) {
+  const float g = scale[1] * (dloss ? dloss[0] : 1.0f);
+  const int64_t total = batch * n * feat;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = (i / feat) % n;
+    float v = 0.0f;
+    if (mask[r]) {
+      const float d = to_f32(y[i]) - to_f32(t[i]);
+      v = d > 0.0f ? g : (d < 0.0f ? -g : 0.0f);   // sign(0) = 0, as torch's L1 backward
+    }
+    dy[i] = from_f32<T>(v);
+  }
+}
+
+}  // namespace
+}  // namespace gwen
+
+using namespace gwen;
+
+extern "C" int gwen_masked_l1_workspace_bytes(int64_t n, size_t* out) {
+  GWEN_CHECK_ARG(out && n >= 0, "bad arguments");
+  *out = static_cast<size_t>(ceil_div(std::max<int64_t>(n, 1), kLossRows)) * sizeof(float2) + 256;
+  return GWEN_OK;
+}
+
+extern "C" int gwen_masked_l1_fwd(const void* y, const void* target, const uint8_t* mask, int64_t batch,
+                                  int64_t n, int64_t feat, int dtype, float* loss_and_scale, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  GWEN_CHECK_ARG(batch >= 0 && n >= 0 && feat >= 0, "negative size");
+  GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
+  GWEN_CHECK_ARG(loss_and_scale && ws && (n == 0 || (y && target && mask)), "null pointer");
+  const int blocks = static_cast<int>(ceil_div(std::max<int64_t>(n, 1), kLossRows));
+  if (ws_bytes < size_t(blocks) * sizeof(float2)) return set_err(GWEN_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float2* part = static_cast<float2*>(ws);
+  if (dtype == GWEN_F32)
+    k_l1_partial<float><<<blocks, kLossThreads, 0, st>>>(static_cast<const float*>(y),
+                                                         static_cast<const float*>(target), mask, batch, n,
+                                                         feat, part);
+  else
+    k_l1_partial<__nv_bfloat16><<<blocks, kLossThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(target), mask, batch, n,
+        feat, part);
+  GWEN_LAUNCH_CHECK("k_l1_partial");
+  k_l1_final<<<1, kLossThreads, 0, st>>>(part, blocks, batch, feat, loss_and_scale);
+  GWEN_LAUNCH_CHECK("k_l1_final");
+  return GWEN_OK;
+}
+
+extern "C" int gwen_masked_l1_bwd(const void* y, const void* target, const uint8_t* mask,
+                                  const float* loss_and_scale, const float* dloss, int64_t batch,
+                                  int64_t n, int64_t feat, int dtype, void* dy, void* stream) {
+  GWEN_CHECK_ARG(batch >= 0 && n >= 0 && feat >= 0, "negative size");
+  GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
+  if (batch * n * feat == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(y && target && mask && loss_and_scale && dy, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>(
+      std::min<int64_t>(ceil_div(batch * n * feat, kLossThreads), int64_t(sm_count()) * 16));
+  if (dtype == GWEN_F32)
+    k_l1_bwd<float><<<blocks, kLossThreads, 0, st>>>(static_cast<const float*>(y),
+                                                     static_cast<const float*>(target), mask,
+                                                     loss_and_scale, dloss, batch, n, feat,
+                                                     static_cast<float*>(dy));
+  else
+    k_l1_bwd<__nv_bfloat16><<<blocks, kLossThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(target), mask,
+        loss_and_scale, dloss, batch, n, feat, static_cast<__nv_bfloat16*>(dy));
+  GWEN_LAUNCH_CHECK("k_l1_bwd");
+  return GWEN_OK;
+}

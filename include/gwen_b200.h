@@ -270,6 +270,24 @@ int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float* db, int64
                        int64_t feat, int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Caller-side loss of the reference training loop: loss_func(output, target, mask) =
+ * L1Loss()(output[mask], target[mask]) (src/gwen/models_gnn.py:261-265, called at :370 with
+ * target = the input features).  Replaces nonzero + two boolean-mask gathers + l1_loss (+ the host
+ * synchronisation the data-dependent size of output[mask] forces) by one pass for the value and
+ * one for the gradient; nothing here synchronises the host.
+ *   y, target : [batch, n, feat] contiguous;  mask : uint8 [n] (torch.bool), shared by the batch
+ *   loss_and_scale : float[2] device: [0] = mean |y - target| over the masked rows (NaN if the mask
+ *                    is empty, like torch), [1] = 1 / (batch * count * feat), read by the backward
+ *   dloss : device scalar gradient of the loss (NULL = 1);  dy = sign(y - target) * mask * dloss * scale */
+int gwen_masked_l1_workspace_bytes(int64_t n, size_t* bytes_out_host);
+int gwen_masked_l1_fwd(const void* y, const void* target, const uint8_t* mask, int64_t batch, int64_t n,
+                       int64_t feat, int dtype, float* loss_and_scale, void* ws, size_t ws_bytes,
+                       void* stream);
+int gwen_masked_l1_bwd(const void* y, const void* target, const uint8_t* mask,
+                       const float* loss_and_scale, const float* dloss, int64_t batch, int64_t n,
+                       int64_t feat, int dtype, void* dy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Halo exchange helpers for the row-band mesh partition (no reference counterpart; SURVEY.md
  * section 8(e)): gather / scatter whole feature rows by index so the send and receive buffers
  * are contiguous for ncclSend / ncclRecv.

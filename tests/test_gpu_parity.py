@@ -609,3 +609,56 @@ def test_host_propagator_matches_device_path(dev, chunks):
         assert torch.equal(o, r.cpu())
     with pytest.raises(RuntimeError):
         hp(torch.empty(h * w, f), outs[0])          # not pinned
+
+
+# ---------------------------------------------------------------------------------------------
+# training-step glue: fused masked L1 loss, train_step
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(154, 24), (3, 154, 24), (1000, 100), (2, 70, 1)])
+def test_masked_l1_loss_matches_reference_loss_func(dev, shape):
+    n = shape[-2]
+    y, t = wts.features(shape, 1), wts.features(shape, 2)
+    t.view(-1)[::7] = y.view(-1)[::7]                              # exact ties: sign(0) = 0
+    mask = torch.arange(n) % 5 == 4
+    yr = y.clone().requires_grad_(True)
+    lr = orc.loss_func(yr, t, mask) if y.dim() == 2 else torch.nn.L1Loss()(yr[:, mask], t[:, mask])
+    (lr * 3.0).backward()
+    yd = y.to(dev).requires_grad_(True)
+    ld = gw.masked_l1_loss(yd, t.to(dev), mask.to(dev))
+    (ld * 3.0).backward()
+    assert abs(ld.item() - lr.item()) <= 1e-6 * abs(lr.item())
+    assert nmax(yd.grad, yr.grad) <= 1e-6
+    assert torch.equal(ld, gw.masked_l1_loss(yd, t.to(dev), mask.to(dev)))   # deterministic
+    # bf16 inputs: same value as the fp32 formula on the rounded inputs
+    yb, tb = y.bfloat16(), t.bfloat16()
+    lb = gw.masked_l1_loss(yb.to(dev), tb.to(dev), mask.to(dev))
+    ref_b = (yb.float() - tb.float()).abs()[..., mask, :].mean()
+    assert abs(lb.item() - ref_b.item()) <= 1e-5 * abs(ref_b.item())
+    # empty mask -> NaN, as the mean of an empty selection
+    assert torch.isnan(gw.masked_l1_loss(yd, t.to(dev), torch.zeros(n, dtype=torch.bool, device=dev)))
+
+
+def test_train_step_matches_oracle_sgd(dev):
+    """Two iterations of the reference inner loop (zero_grad / forward / loss vs the input / backward /
+    optimizer.step) with our layers + fused loss == the oracle model + reference loss_func on the CPU."""
+    ei, n, c, hid = orc.grid(14, 11), 154, 24, 64
+    ref = orc.GNNModelOracle(c, c, hid)
+    wts.fill_model_(ref, 4)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    model = gw.GNNModel(cfg)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    x = wts.features((n, c), 6)
+    mask = torch.arange(n) % 5 == 4
+    opt_r = torch.optim.SGD(ref.parameters(), lr=0.05)
+    opt_d = torch.optim.SGD(model.parameters(), lr=0.05)
+    for _ in range(2):
+        opt_r.zero_grad()
+        lr = orc.loss_func(ref(x, ei), x, mask)
+        lr.backward()
+        opt_r.step()
+        ld = gw.train_step(model, x.to(dev), ei.to(dev), mask.to(dev), opt_d)
+        assert abs(ld.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    got = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        assert nmax(got[name].detach(), p.detach()) <= 1e-5, name
