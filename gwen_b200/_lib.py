@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu"]
-HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu"]
+HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
 GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4
@@ -96,6 +96,7 @@ PROTOTYPES = {
                                      _i64, _i64, _int, _p, _int, _i32, _i32, _p]),
     "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                           _int, _p, _int, _i32, _i32, C.POINTER(HaloPeersStruct), _p]),
+    "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,

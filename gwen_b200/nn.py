@@ -31,7 +31,11 @@ class _GCNConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], graph: GraphCSR,
                 relu: bool, agg_first: bool):
-        if agg_first:      # (A_hat x) W^T: aggregate at the narrower input width
+        fused = agg_first and ops.gcn_fused_preferred(graph, x, weight)
+        if fused:          # (A_hat x) W^T in ONE kernel: the aggregated rows never leave the SM
+            y = ops.gcn_fused(graph, x, weight, bias, relu)
+            saved_in = x   # backward recomputes A_hat x (one narrow stencil) instead of storing it
+        elif agg_first:    # (A_hat x) W^T: aggregate at the narrower input width
             h = ops.aggregate(graph, x)
             y = ops.linear(h, weight, bias, relu)
             saved_in = h
@@ -39,7 +43,7 @@ class _GCNConvFn(torch.autograd.Function):
             h = ops.linear(x, weight)
             y = ops.aggregate(graph, h, bias, relu)
             saved_in = x
-        ctx.graph, ctx.relu, ctx.agg_first = graph, relu, agg_first
+        ctx.graph, ctx.relu, ctx.agg_first, ctx.fused = graph, relu, agg_first, fused
         ctx.has_bias = bias is not None
         ctx.save_for_backward(saved_in, weight, y if relu else None)
         return y
@@ -55,6 +59,8 @@ class _GCNConvFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dx = None
         if ctx.agg_first:
+            if ctx.fused:
+                saved_in = ops.aggregate(ctx.graph, saved_in)     # recompute A_hat x
             dw = ops.linear_bwd_weight(dy, saved_in)              # dW = dy^T (A_hat x)
             if need_dx:
                 dx = ops.aggregate(graph_t, ops.linear_bwd_data(dy, weight))

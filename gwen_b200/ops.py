@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
-__all__ = ["aggregate", "mesh_stencil", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd",
+__all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd",
            "rows_gather", "rows_scatter_", "dtype_code"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
@@ -138,6 +138,50 @@ def _rows_view(t: torch.Tensor):
         return t.view((-1,) + tuple(t.shape[-2:]))
     except RuntimeError:
         return None
+
+
+# The fused layer kernel pays off once every CTA pair has a long queue of 8 x 32 tiles (measured on
+# 1158 x 774 meshes: -4 % .. -11 % vs the two-kernel path; on 582 x 390 it is slower).
+FUSED_MIN_ITEMS = 3500
+
+
+def gcn_fused_supported(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """True when ``gcn_fused`` can serve this layer: plain mesh, bf16, k_in in {64, 128, 192, 256},
+    n_out a multiple of 128 (and GWEN_NO_FUSED unset)."""
+    import os
+    k, n = weight.shape[1], weight.shape[0]
+    return (os.environ.get("GWEN_NO_FUSED") is None and graph.is_plain_mesh and x.dtype == torch.bfloat16
+            and x.is_cuda and 64 <= k <= 256 and k % 64 == 0 and n % 128 == 0 and n <= 8192)
+
+
+def gcn_fused_preferred(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Supported AND large enough to beat the two-kernel path (the layer's automatic choice)."""
+    if not gcn_fused_supported(graph, x, weight):
+        return False
+    h, w = graph.grid_shape
+    batch = x.numel() // max(1, x.shape[-1] * x.shape[-2])
+    return batch * ((h + 7) // 8) * ((w + 31) // 32) >= FUSED_MIN_ITEMS
+
+
+def gcn_fused(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epi((A_hat x) W^T + bias) in one kernel (gwen_gcn_fused_fwd); x [..., N, K] bf16."""
+    _require_cuda(x, "x")
+    x3, lead = _as_3d(x)
+    b, n, k = x3.shape
+    h, w = graph.grid_shape
+    n_out = weight.shape[0]
+    wt = weight.detach().to(x3.dtype).contiguous()
+    bias32 = _bias32(bias)
+    dpad = graph.dis_padded()
+    with torch.cuda.device(x3.device):
+        if out is None:
+            out = torch.empty((b, n, n_out), dtype=x3.dtype, device=x3.device)
+        assert out.is_contiguous()
+        check(lib().gwen_gcn_fused_fwd(_ptr(x3), _ptr(wt), _ptr(out), _ptr(dpad), dpad.shape[1], b, h, w, k,
+                                       n_out, dtype_code(x3.dtype), _ptr(bias32),
+                                       _lib.EPI_RELU if relu else 0, _stream()), "gwen_gcn_fused_fwd")
+    return out.reshape(tuple(lead) + (n, n_out))
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,

@@ -233,6 +233,20 @@ int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded, int6
                                const gwen_halo_peers* peers, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1 + K2 fused (mesh graphs, bf16): y = epi( (A_hat x) W^T + bias ) in ONE kernel -- the whole
+ * GCNConv.forward for the layers that aggregate before they project
+ * (in_channels < out_channels).  CUDA-core warps run the mesh stencil of gwen_grid_stencil_fwd on
+ * TMA-staged source boxes and write the aggregated rows into shared memory as the tcgen05 A operand;
+ * the projection is the CTA-pair GEMM of gwen_linear_fwd.  The aggregated intermediate is rounded to
+ * bf16 exactly as the two-kernel path stores it, so results match that path.
+ *   x : bf16 [B, h*w, k_in] contiguous      weight : bf16 [n_out, k_in]      y : bf16 [B, h*w, n_out]
+ *   dis_padded / dis_pitch : as for gwen_grid_stencil_fwd
+ *   k_in in {64, 128, 192, 256}, n_out % 128 == 0 (else GWEN_E_NOSUPPORT: use the two kernels) */
+int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* dis_padded,
+                       int64_t dis_pitch, int64_t batch, int64_t h, int64_t w, int64_t k_in,
+                       int64_t n_out, int dtype, const float* bias, int epilogue, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
  * SURVEY.md table 2.3 row 6) and, through the epilogue, the bias add and ReLU when the
  * projection runs after the aggregation:

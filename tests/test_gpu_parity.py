@@ -662,3 +662,54 @@ def test_train_step_matches_oracle_sgd(dev):
     got = dict(model.named_parameters())
     for name, p in ref.named_parameters():
         assert nmax(got[name].detach(), p.detach()) <= 1e-5, name
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 + K2 fused layer kernel (mesh graphs, bf16)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(8, 32), (9, 33), (17, 23), (40, 70), (3, 5), (64, 130)])
+@pytest.mark.parametrize("k,n,batch", [(64, 1024, 1), (256, 512, 2), (192, 1024, 1), (128, 128, 3), (256, 256, 1)])
+def test_fused_layer_matches_two_kernel_path(dev, hw, k, n, batch):
+    """gwen_gcn_fused_fwd == stencil aggregation followed by the tcgen05 projection (same bf16
+    rounding of the aggregated rows, same MMA order): bitwise on the mesh, incl. tiles that overhang
+    it; and within bf16 tolerance of the fp32 oracle."""
+    h, w = hw
+    ei = orc.grid(h, w)
+    g = gw.build_graph(ei.to(dev), h * w)
+    x = wts.features((batch, h * w, k), 31).bfloat16()
+    wt, b = wts.glorot(n, k, 32).bfloat16(), wts.small_bias(n, 33)
+    assert ops.gcn_fused_supported(g, x.to(dev), wt.to(dev))
+    y = ops.gcn_fused(g, x.to(dev), wt.to(dev), b.to(dev), relu=True)
+    hh = ops.aggregate(g, x.to(dev), kernel="stencil")
+    y2 = ops.linear(hh, wt.to(dev), b.to(dev), relu=True)
+    assert y.shape == y2.shape == (batch, h * w, n)
+    assert torch.equal(y, y2)
+    assert torch.equal(y, ops.gcn_fused(g, x.to(dev), wt.to(dev), b.to(dev), relu=True))      # deterministic
+    if h * w <= 1500:
+        ref = torch.relu(oracle_aggregate(x[0].float(), ei, h * w) @ wt.float().t() + b)
+        assert nmax(y[0].float(), ref) <= BF16_TOL
+    # no bias, no relu
+    assert torch.equal(ops.gcn_fused(g, x.to(dev), wt.to(dev)), ops.linear(hh, wt.to(dev)))
+
+
+def test_fused_layer_autograd_matches_unfused(dev, monkeypatch):
+    monkeypatch.setattr(ops, "FUSED_MIN_ITEMS", 0)        # force the fused choice on a small mesh
+    h, w, k, n = 21, 19, 64, 256
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    x = wts.features((2, h * w, k), 41).bfloat16().to(dev)
+    conv = gw.GCNConv(k, n).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        conv.bias.copy_(wts.small_bias(n, 42))
+    t = wts.features((2, h * w, n), 43).bfloat16().to(dev)
+
+    def run():
+        conv.zero_grad()
+        xx = x.clone().requires_grad_(True)
+        y = conv(xx, g, relu=True)
+        (y.float() * t.float()).sum().backward()
+        return y.detach(), xx.grad, conv.lin.weight.grad.clone(), conv.bias.grad.clone()
+    a = run()
+    monkeypatch.setenv("GWEN_NO_FUSED", "1")
+    bref = run()
+    for u, v in zip(a, bref):
+        assert torch.equal(u, v)
