@@ -1,4 +1,5 @@
-"""Functional wrappers over the C ABI: aggregate (K1), linear (K2), backward pieces, row moves.
+"""Functional wrappers over the C ABI: aggregate (K1), linear (K2), the fused layer, backward
+pieces, row moves.
 
 Every function takes CUDA tensors, launches on the current stream of the tensors' device and
 returns a torch-allocated result.  Nothing here computes with torch ops: a missing library or a
@@ -15,7 +16,8 @@ from . import _lib
 from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
-__all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred", "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd",
+__all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred",
+           "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd",
            "rows_gather", "rows_scatter_", "dtype_code"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
