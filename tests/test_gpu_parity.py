@@ -713,3 +713,30 @@ def test_fused_layer_autograd_matches_unfused(dev, monkeypatch):
     bref = run()
     for u, v in zip(a, bref):
         assert torch.equal(u, v)
+
+
+def test_graph_dataset_matches_reference_tensorisation(dev):
+    """GraphDataset (utils.py:164-211 mirror) on the reference's own sample data: x of every time step
+    equals the golden stacking, the member split follows np.random.shuffle, the graph is K_members."""
+    import numpy as np
+    gx = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_x.npy"))     # [2, 2, 100]
+    theta = gx.reshape(2, 2, 10, 10)                                                  # t, member, h, cell
+    np.random.seed(23)
+    want = np.arange(2)
+    np.random.shuffle(want)
+    np.random.seed(23)
+    torch.manual_seed(23)
+    ds = gw.GraphDataset(theta, split=1, device=dev)
+    assert ds.len() == 2 and ds.nodes == 2 and ds.channels == 100
+    assert list(ds.input_indices) == list(want[:1]) and list(ds.target_indices) == list(want[1:])
+    assert ds.edge_index.cpu().tolist() == [[0, 1], [1, 0]]
+    for t in range(2):
+        d = ds.get(t)
+        assert torch.equal(d.x.cpu(), torch.from_numpy(gx[t]))
+        assert d.target_mask.cpu().tolist() == [i in set(ds.target_indices) for i in range(2)]
+    # and the sample flows through the model + train step
+    cfg = gw.GNNConfig(nodes_in=2, nodes_out=2, channels_in=100, channels_out=100, hidden_feats=64)
+    model = gw.GNNModel(cfg).to(dev)
+    d = ds.get(0)
+    loss = gw.train_step(model, d.x, d.edge_index, d.target_mask)
+    assert torch.isfinite(loss)
