@@ -480,6 +480,20 @@ class BandGNNModel(torch.nn.Module):
             x = _BandGCNFn.apply(x, conv.lin.weight, conv.bias, self, li, relu, self._agg_first[li])
         return x if x_own.dim() == 3 else x[0]
 
+    def loss(self, y_own: torch.Tensor, target_own: torch.Tensor, mask_own: torch.Tensor) -> torch.Tensor:
+        """This rank's share of the reference ``loss_func`` (masked L1, ``models_gnn.py:261-265``) over the
+        WHOLE mesh: local masked mean x (local count / global count), so the shares of all ranks add up
+        to the global masked mean and ``backward`` + :meth:`allreduce_grads` gives its gradient.  The
+        count of masked nodes is all-reduced once per mask and cached."""
+        from .train import masked_l1_loss
+        key = (mask_own.data_ptr(), mask_own._version)
+        if getattr(self, "_mask_key", None) != key:
+            cnt = mask_own.sum().to(torch.float64).reshape(1)
+            tot = cnt.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.band.group)
+            self._mask_key, self._mask_share = key, (cnt / tot.clamp_min(1.0)).to(torch.float32)
+        return masked_l1_loss(y_own, target_own, mask_own) * self._mask_share[0]
+
     def allreduce_grads(self) -> None:
         """Sum the parameter gradients over the ranks (one flat NCCL all-reduce)."""
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]

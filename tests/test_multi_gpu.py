@@ -40,4 +40,4 @@ def test_band_model_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
-    assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4
+    assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4 and out["loss_rel_err"] < 1e-5
