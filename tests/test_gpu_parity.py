@@ -740,3 +740,42 @@ def test_graph_dataset_matches_reference_tensorisation(dev):
     d = ds.get(0)
     loss = gw.train_step(model, d.x, d.edge_index, d.target_mask)
     assert torch.isfinite(loss)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE full sizes through size-independent properties
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(1158, 774), (2048, 2048)])
+def test_full_size_mesh_operator_properties(dev, hw):
+    """Config 3 / config 4 meshes (too large for the CPU oracle in seconds): the normalised mesh
+    operator must (a) give row sums dis[d] * sum_{s in N(d)} dis[s] on a constant input -- checked
+    against degrees known in closed form, (b) be self-adjoint <A x, y> = <x, A y>, (c) be linear, and
+    (d) agree between the stencil kernel and the generic CSR kernel on the same graph handle."""
+    h, w = hw
+    n, f = h * w, 8
+    g = gw.get_graph(gw.grid(h, w, dev), n)
+    assert g.is_plain_mesh and g.num_messages == gw.grid_edge_count(h, w)
+    # (a) closed-form degrees of the 8-neighbour mesh incl. self loop: 4 corners, 6 edges, 9 interior
+    r = torch.arange(h, device=dev).view(-1, 1)
+    c = torch.arange(w, device=dev).view(1, -1)
+    deg = ((1 + (r > 0).long() + (r < h - 1).long()) * (1 + (c > 0).long() + (c < w - 1).long())).double()
+    dis = deg.pow(-0.5)
+    assert torch.equal(g.dis.view(h, w), dis.float())                      # K0: fp64 1/sqrt(deg) rounded once
+    ones = torch.ones(n, f, device=dev)
+    pad = torch.nn.functional.pad(dis, (1, 1, 1, 1))
+    box = sum(pad[1 + dr:h + 1 + dr, 1 + dc:w + 1 + dc] for dr in (-1, 0, 1) for dc in (-1, 0, 1))
+    want = (dis * box).reshape(n, 1)
+    got = ops.aggregate(g, ones, kernel="stencil")
+    assert nmax(got[:, :1], want) <= STENCIL_TOL
+    # (b) adjointness and (c) linearity on random vectors, fp64 inner products
+    gen = torch.Generator(dev).manual_seed(3)
+    x = torch.randn(n, f, device=dev, generator=gen)
+    y = torch.randn(n, f, device=dev, generator=gen)
+    ax, ay = ops.aggregate(g, x, kernel="stencil"), ops.aggregate(g, y, kernel="stencil")
+    lhs, rhs = (ax.double() * y.double()).sum(), (x.double() * ay.double()).sum()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+    axy = ops.aggregate(g, 2.0 * x - 0.5 * y, kernel="stencil")
+    assert nmax(axy, 2.0 * ax.double() - 0.5 * ay.double()) <= 2e-6
+    # (d) stencil vs the bit-exact CSR kernel
+    assert nmax(ax, ops.aggregate(g, x, kernel="rows")) <= STENCIL_TOL
+    gw.clear_graph_cache()
