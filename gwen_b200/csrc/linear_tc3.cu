@@ -44,6 +44,7 @@ struct Tc3Args {
   const float* bias;
   int64_t m;
   int n, k_blocks, bn, stages, relu, bufs, row_major_tiles;
+  int epi_groups;  // epilogue warp groups (of 4 warps) that work: 4, or 2 to trade staging for ring depth
   int b_mn;  // B operand is MN-major: w is [reduction][n] row-major (dgrad: dx = dy W)
 };
 
@@ -62,7 +63,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
   const uint32_t staging = base + uint32_t(g.stages) * stage_bytes;  // 16 warps x bufs x 2 KB
   // the whole bias vector (n floats, zeros when absent) sits behind the staging buffers
   float* bias_s = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) +
-                                           size_t(kEpiWarps) * 2048u * size_t(g.bufs));
+                                           size_t(4 * g.epi_groups) * 2048u * size_t(g.bufs));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.n / g.bn;
   const int n_sub = g.bn / 32;  // 32-column epilogue sub-chunks per tile
@@ -86,7 +87,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
     }
   };
   const uint32_t tmem_cols = uint32_t(2 * g.bn);
-  const uint32_t epi_arrivals = 2u * 4u * uint32_t(n_sub < 4 ? n_sub : 4);
+  const uint32_t epi_arrivals = 2u * 4u * uint32_t(n_sub < g.epi_groups ? n_sub : g.epi_groups);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&amap);
@@ -177,7 +178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
     const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     uint32_t seq = 0, buf = 0;
-    if (g4 < n_sub) {
+    if (g4 < n_sub && g4 < g.epi_groups) {
       for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
         int mb, nt;
         tile_of(idx, mb, nt);
@@ -187,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
         mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
-        for (int sc = g4; sc < n_sub; sc += 4) {
+        for (int sc = g4; sc < n_sub; sc += g.epi_groups) {
           const int c = sc * 32;
           uint32_t r[32];
           tmem_ld32_nowait(t_addr + uint32_t(c), r);
@@ -197,7 +198,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (sc + 4 >= n_sub) {  // last TMEM read of this tile by this warp
+          if (sc + g.epi_groups >= n_sub) {  // last TMEM read of this tile by this warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc ? empty_remote1 : empty_remote0);
@@ -267,7 +268,14 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
     const char* v = getenv("GWEN_TC3_BUFS");
     return v && atoi(v) == 2 ? 2 : 1;
   }();
-  const size_t staging_bytes = size_t(kEpiWarps) * bufs * 2048 + align_up(size_t(n_out) * 4, 1024);
+  // deep reductions are MMA-bound and want ring depth (6 stages need the room of 8 staging buffers);
+  // shallow ones are store-bound and want all 16 epilogue warps
+  static const int groups_env = [] {
+    const char* v = getenv("GWEN_TC3_EPI_GROUPS");
+    return v ? atoi(v) : 0;
+  }();
+  const int epi_groups = (groups_env == 2 || groups_env == 4) ? groups_env : (k >= 512 ? 2 : 4);
+  const size_t staging_bytes = size_t(4 * epi_groups) * bufs * 2048 + align_up(size_t(n_out) * 4, 1024);
   static const int stage_cap = [] {
     const char* v = getenv("GWEN_TC3_STAGES");
     return v ? std::max(2, std::min(kMaxStages, atoi(v))) : kMaxStages;
@@ -284,7 +292,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   }();
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
-  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, b_mn};
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, b_mn};
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);
