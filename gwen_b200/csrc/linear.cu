@@ -30,6 +30,13 @@ int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t ld
 int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st);
 
+// linear_tf32x3.cu
+int linear_tf32x3_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                            const void* x, const void* w, const void* y);
+size_t linear_tf32x3_workspace_bytes(int64_t m, int64_t k, int64_t n_out);
+int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
+                      int64_t ldy, const float* bias, int relu, void* ws, size_t ws_bytes,
+                      cudaStream_t st);
 // linear_wgrad_tc.cu
 int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
                               const void* dy, const void* x);
@@ -363,6 +370,26 @@ extern "C" int gwen_linear_fwd(const void* x, const void* weight, void* y, int64
   GemmArgs g{x, weight, y, bias, m, n_out, k, ldx, ldw, ldy, k, 0, relu};
   return dtype == GWEN_F32 ? launch_gemm<float, true, true, false>(g, 1, st)
                            : launch_gemm<__nv_bfloat16, true, true, false>(g, 1, st);
+}
+
+extern "C" int gwen_linear_fwd_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype,
+                                               size_t* out) {
+  GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
+  *out = (dtype == GWEN_F32 && m >= 4096 && k >= 32 && k % 4 == 0 && n_out % 64 == 0)
+             ? linear_tf32x3_workspace_bytes(m, k, n_out) : 0;
+  return GWEN_OK;
+}
+
+extern "C" int gwen_linear_fwd_ws(const void* x, const void* weight, void* y, int64_t m, int64_t k,
+                                  int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int dtype,
+                                  const float* bias, int epilogue, void* ws, size_t ws_bytes,
+                                  void* stream) {
+  if (dtype == GWEN_F32 && ws && m > 0 && x && weight && y &&
+      linear_tf32x3_supported(m, k, n_out, ldx, ldw, ldy, x, weight, y) &&
+      ws_bytes >= linear_tf32x3_workspace_bytes(m, k, n_out))
+    return linear_tf32x3_fwd(x, weight, y, m, k, n_out, ldy, bias, (epilogue & GWEN_EPI_RELU) ? 1 : 0, ws,
+                             ws_bytes, static_cast<cudaStream_t>(stream));
+  return gwen_linear_fwd(x, weight, y, m, k, n_out, ldx, ldw, ldy, dtype, bias, epilogue, stream);
 }
 
 extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m,

@@ -222,9 +222,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     x2 = x.reshape(-1, k).contiguous()
     with torch.cuda.device(x2.device):
         y = torch.empty((x2.shape[0], n_out), dtype=x2.dtype, device=x2.device)
-        check(lib().gwen_linear_fwd(_ptr(x2), _ptr(wt), _ptr(y), x2.shape[0], k, n_out, k, k, n_out,
-                                    code, _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
-              "gwen_linear_fwd")
+        need = C.c_size_t(0)
+        if x2.dtype == torch.float32:      # fp32 on the tensor cores (3xTF32) needs scratch for the split operands
+            check(lib().gwen_linear_fwd_workspace_bytes(x2.shape[0], k, n_out, code, C.byref(need)), "linear ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=x2.device) if need.value else None
+        check(lib().gwen_linear_fwd_ws(_ptr(x2), _ptr(wt), _ptr(y), x2.shape[0], k, n_out, k, k, n_out,
+                                       code, _ptr(bias32), _lib.EPI_RELU if relu else 0, _ptr(ws), need.value,
+                                       _stream()), "gwen_linear_fwd")
     return y.reshape(tuple(x.shape[:-1]) + (n_out,))
 
 

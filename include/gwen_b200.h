@@ -260,6 +260,14 @@ int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* 
 int gwen_linear_fwd(const void* x, const void* weight, void* y, int64_t m, int64_t k,
                     int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int dtype,
                     const float* bias, int epilogue, void* stream);
+/* gwen_linear_fwd with a scratch buffer: fp32 problems with m >= 4096, k % 4 == 0, n_out % 64 == 0 and
+ * dense rows then run on the tensor cores as three kind::tf32 products per K step (operands split once
+ * into hi / lo TF32 parts in the workspace, fp32 accumulation: fp32-level accuracy, ~1e-6 relative);
+ * everything else (and a NULL / too small workspace, or GWEN_FP32_SIMT set) is gwen_linear_fwd. */
+int gwen_linear_fwd_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype, size_t* bytes_out_host);
+int gwen_linear_fwd_ws(const void* x, const void* weight, void* y, int64_t m, int64_t k, int64_t n_out,
+                       int64_t ldx, int64_t ldw, int64_t ldy, int dtype, const float* bias, int epilogue,
+                       void* ws, size_t ws_bytes, void* stream);
 int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
                          void* stream);

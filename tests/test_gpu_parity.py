@@ -243,8 +243,11 @@ def test_aggregate_is_deterministic(dev):
 # K2 linear (vs a plain PyTorch fp32 reference of the same op)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("m,k,n", [(2, 100, 1024), (300, 64, 1024), (257, 1024, 512), (1000, 512, 256),
-                                   (130, 37, 19), (1, 1, 1), (4096, 256, 256)])
+                                   (130, 37, 19), (1, 1, 1), (4096, 256, 256), (20000, 512, 1024),
+                                   (70001, 1024, 256), (4096, 36, 64), (5000, 64, 192), (9000, 100, 128)])
 def test_linear_fp32(dev, m, k, n):
+    """fp32 projection: CUDA-core GEMM for small / ragged problems, 3xTF32 tensor-core GEMM (fp32-level
+    accuracy) for m >= 4096 with k % 4 == 0 and n % 64 == 0 -- both within the fp32 parity bar."""
     x, w, b = wts.features((m, k), 1), wts.glorot(n, k, 2), wts.small_bias(n, 3)
     ref = torch.relu(x.double() @ w.double().t() + b.double())
     y = ops.linear(x.to(dev), w.to(dev), b.to(dev), relu=True)
