@@ -26,7 +26,7 @@ EPI_NONE, EPI_RELU = 0, 1
 def nvcc_command(out_path: str = LIB_PATH) -> list:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-            "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+            "--expt-relaxed-constexpr", "--threads", "0", "-Xcompiler", "-fPIC", "-shared",
             "-I" + os.path.join(_ROOT, "include"), "-o", out_path] + \
         [os.path.join(CSRC, s) for s in SOURCES]
 
