@@ -376,7 +376,7 @@ extern "C" int gwen_linear_fwd_workspace_bytes(int64_t m, int64_t k, int64_t n_o
                                                size_t* out) {
   GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
   *out = (dtype == GWEN_F32 && m >= 4096 && k >= 32 && k % 4 == 0 && n_out % 64 == 0)
-             ? linear_tf32x3_workspace_bytes(m, k, n_out) : 0;
+             ? linear_tf32x3_workspace_bytes(m, k, n_out) : 0;   // the split copy of W
   return GWEN_OK;
 }
 

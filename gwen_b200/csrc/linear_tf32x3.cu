@@ -6,9 +6,12 @@
 //   hi = x with the low 13 mantissa bits cleared   (exactly a TF32 value)
 //   lo = (x - hi) with its low 13 bits cleared     (exact difference, next 10-11 bits)
 // and accumulate  lo_a * hi_b + hi_a * lo_b + hi_a * hi_b  in the fp32 TMEM accumulator: the dropped
-// terms are O(2^-21) relative, i.e. fp32-level.  k_split_tf32 writes the four arrays (one pass over x
-// and W); the GEMM is the CTA-pair pipeline of linear_tc3.cu with four operand tiles per stage
-// (128 B = 32 fp32 per swizzle row), K = 8 per MMA, and an fp32 TMA-store epilogue.
+// terms are O(2^-21) relative, i.e. fp32-level.  W is split once per call by k_split_tf32 (it is
+// small); x is split IN the kernel: the raw fp32 tile lands by TMA, four transform warps rewrite it
+// in place as hi and write lo next to it (the split is elementwise, so the swizzled layout does not
+// matter), fence.proxy.async, and arrive on the leader's xf[stage] barrier.  Otherwise this is the
+// CTA-pair pipeline of linear_tc3.cu with four operand tiles per stage (128 B = 32 fp32 per swizzle
+// row), K = 8 per MMA, and an fp32 TMA-store epilogue.
 #include <algorithm>
 #include <cstdlib>
 
@@ -21,7 +24,8 @@ using namespace tc;
 namespace {
 
 constexpr int kEpiWarpsF = 16;
-constexpr int kTfThreads = 64 + 32 * kEpiWarpsF;
+constexpr int kXfWarps = 4;      // transform warps (split the A tile into hi / lo in shared memory)
+constexpr int kTfThreads = 64 + 32 * kXfWarps + 32 * kEpiWarpsF;
 constexpr int BKF = 32;          // fp32 elements per K block = one 128-byte swizzle row
 constexpr int UMMA_KF = 8;       // kind::tf32
 constexpr int kMaxStagesF = 6;
@@ -73,12 +77,14 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
-    k_linear_tf32x3(const __grid_constant__ CUtensorMap ahi, const __grid_constant__ CUtensorMap alo,
-                    const __grid_constant__ CUtensorMap bhi, const __grid_constant__ CUtensorMap blo,
-                    const __grid_constant__ CUtensorMap ymap, TfArgs g) {
+    k_linear_tf32x3(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bhi,
+                    const __grid_constant__ CUtensorMap blo, const __grid_constant__ CUtensorMap ymap,
+                    TfArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStagesF], empty_bar[kMaxStagesF], tmem_full_bar[2],
-      tmem_empty_bar[2];
+  // full_a: this CTA's raw x tile has landed (local); xf: both CTAs' tiles are split (leader's is used);
+  // full_b: both CTAs' W hi / lo halves have landed (leader's is used)
+  __shared__ __align__(8) uint64_t full_a[kMaxStagesF], xf_bar[kMaxStagesF], full_b[kMaxStagesF],
+      empty_bar[kMaxStagesF], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t rank = cluster_ctarank();
@@ -96,13 +102,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
   const uint32_t epi_arrivals = 2u * 4u * uint32_t(n_sub < 4 ? n_sub : 4);
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&ahi);
-    tma_prefetch_desc(&alo);
+    tma_prefetch_desc(&amap);
     tma_prefetch_desc(&bhi);
     tma_prefetch_desc(&blo);
     tma_prefetch_desc(&ymap);
     for (int i = 0; i < g.stages; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&full_a[i]), 1);
+      mbar_init(smem_u32(&xf_bar[i]), 2 * kXfWarps);
+      mbar_init(smem_u32(&full_b[i]), 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -133,11 +140,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
           const uint32_t s = it % uint32_t(g.stages), round = it / uint32_t(g.stages);
           if (round > 0) mbar_wait(smem_u32(&empty_bar[s]), (round - 1) & 1u);
-          if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * stage_bytes);
-          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
           const uint32_t dst = base + s * stage_bytes;
-          tma_load_3d_pair(dst, &ahi, kb * BKF, m0, 0, bar);
-          tma_load_3d_pair(dst + a_bytes, &alo, kb * BKF, m0, 0, bar);
+          mbar_expect_tx(smem_u32(&full_a[s]), a_bytes);            // raw x tile: local barrier
+          tma_load_3d(dst, &amap, kb * BKF, m0, 0, smem_u32(&full_a[s]));
+          if (leader) mbar_expect_tx(smem_u32(&full_b[s]), 4 * b_bytes);
+          const uint32_t bar = mapa_u32(smem_u32(&full_b[s]), 0);
           tma_load_3d_pair(dst + 2 * a_bytes, &bhi, kb * BKF, n0, 0, bar);
           tma_load_3d_pair(dst + 2 * a_bytes + b_bytes, &blo, kb * BKF, n0, 0, bar);
         }
@@ -153,8 +160,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
         tc_fence_after();
         const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-          const uint32_t s = it % uint32_t(g.stages);
-          mbar_wait(smem_u32(&full_bar[s]), (it / uint32_t(g.stages)) & 1u);
+          const uint32_t s = it % uint32_t(g.stages), par = (it / uint32_t(g.stages)) & 1u;
+          mbar_wait(smem_u32(&full_b[s]), par);
+          mbar_wait(smem_u32(&xf_bar[s]), par);
           tc_fence_after();
           const uint32_t st0 = base + s * stage_bytes;
           const uint64_t d_ahi = make_smem_desc(st0), d_alo = make_smem_desc(st0 + a_bytes);
@@ -172,10 +180,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
         umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
       }
     }
+  } else if (warp < 2 + kXfWarps) {
+    // ===== transform warps: raw fp32 tile -> hi (in place) + lo (next slot), 16 bytes per step =====
+    const int t = int(threadIdx.x) - 64;                      // 0 .. 127
+    const uint32_t xf_remote_base = mapa_u32(smem_u32(&xf_bar[0]), 0);
+    uint32_t it = 0;
+    for (int64_t tile = cluster_id; tile < total; tile += n_clusters) {
+      for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+        const uint32_t s = it % uint32_t(g.stages), par = (it / uint32_t(g.stages)) & 1u;
+        mbar_wait(smem_u32(&full_a[s]), par);
+        const uint32_t a_hi = base + s * stage_bytes + uint32_t(t) * 16u, a_lo = a_hi + a_bytes;
+#pragma unroll
+        for (int j = 0; j < int(BM * 128 / 16 / (32 * kXfWarps)); ++j) {   // 1024 uint4 / 128 threads
+          const uint32_t off = uint32_t(j) * (32u * kXfWarps * 16u);
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_hi + off));
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = u[e] & 0xFFFFE000u;
+            l[e] = __float_as_uint(__uint_as_float(u[e]) - __uint_as_float(h[e])) & 0xFFFFE000u;
+          }
+          sts_v4(a_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
+          sts_v4(a_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(xf_remote_base + s * 8u);
+      }
+    }
   } else {
-    // ===== epilogue warps 2..17: TMEM lanes 32*(warp%4) .. +31, 16-column sub-chunks g4, g4+4, .. =====
-    const int q = warp & 3, g4 = (warp - 2) >> 2;
-    const uint32_t my_stage = staging + uint32_t(warp - 2) * 2048u;
+    // ===== epilogue warps 6..21: TMEM lanes 32*(warp%4) .. +31, 16-column sub-chunks g4, g4+4, .. =====
+    const int q = warp & 3, g4 = (warp - 2 - kXfWarps) >> 2;
+    const uint32_t my_stage = staging + uint32_t(warp - 2 - kXfWarps) * 2048u;
     const uint32_t row_off = uint32_t(lane) * 64u;
     const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B
     const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
@@ -246,7 +285,8 @@ int linear_tf32x3_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, in
 }
 
 size_t linear_tf32x3_workspace_bytes(int64_t m, int64_t k, int64_t n_out) {
-  return 2 * (align_up(size_t(m) * k * 4, 256) + align_up(size_t(n_out) * k * 4, 256));
+  (void)m;
+  return 2 * align_up(size_t(n_out) * k * 4, 256);   // W hi / lo (x is split inside the kernel)
 }
 
 int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
@@ -254,23 +294,16 @@ int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t 
                       cudaStream_t st) {
   if (ws_bytes < linear_tf32x3_workspace_bytes(m, k, n_out))
     return set_err(GWEN_E_WORKSPACE, "tf32x3 workspace too small");
-  const size_t xa = align_up(size_t(m) * k * 4, 256), wa = align_up(size_t(n_out) * k * 4, 256);
-  float* x_hi = static_cast<float*>(ws);
-  float* x_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + xa);
-  float* w_hi = reinterpret_cast<float*>(static_cast<char*>(ws) + 2 * xa);
-  float* w_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + 2 * xa + wa);
-  const int64_t x4 = m * k / 4, w4 = n_out * k / 4;
-  k_split_tf32<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(x4, 256), int64_t(sm_count()) * 16)), 256, 0, st>>>(
-      static_cast<const float*>(x), x_hi, x_lo, x4);
-  GWEN_LAUNCH_CHECK("k_split_tf32");
+  const size_t wa = align_up(size_t(n_out) * k * 4, 256);
+  float* w_hi = static_cast<float*>(ws);
+  float* w_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + wa);
+  const int64_t w4 = n_out * k / 4;
   k_split_tf32<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(w4, 256), int64_t(sm_count()) * 16)), 256, 0, st>>>(
       static_cast<const float*>(w), w_hi, w_lo, w4);
   GWEN_LAUNCH_CHECK("k_split_tf32");
   const int bn = n_out % 128 == 0 ? 128 : 64;
-  CUtensorMap ahi, alo, bhi, blo, ymap;
-  int rc = make_tensor_map_3d(&ahi, x_hi, GWEN_F32, k, m, 1, k, 0, BKF, BM, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc != GWEN_OK) return rc;
-  rc = make_tensor_map_3d(&alo, x_lo, GWEN_F32, k, m, 1, k, 0, BKF, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap amap, bhi, blo, ymap;
+  int rc = make_tensor_map_3d(&amap, x, GWEN_F32, k, m, 1, k, 0, BKF, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
   rc = make_tensor_map_3d(&bhi, w_hi, GWEN_F32, k, n_out, 1, k, 0, BKF, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
@@ -288,7 +321,7 @@ int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t 
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t total = ceil_div(m, 2 * BM) * (n_out / bn);
   const int pairs = static_cast<int>(std::min<int64_t>(total, std::max(1, (sm_count() - sm_reserve()) / 2)));
-  k_linear_tf32x3<<<2 * pairs, kTfThreads, smem, st>>>(ahi, alo, bhi, blo, ymap, g);
+  k_linear_tf32x3<<<2 * pairs, kTfThreads, smem, st>>>(amap, bhi, blo, ymap, g);
   GWEN_LAUNCH_CHECK("k_linear_tf32x3");
   return GWEN_OK;
 }
