@@ -782,3 +782,26 @@ def test_full_size_mesh_operator_properties(dev, hw):
     # (d) stencil vs the bit-exact CSR kernel
     assert nmax(ax, ops.aggregate(g, x, kernel="rows")) <= STENCIL_TOL
     gw.clear_graph_cache()
+
+
+def test_linear_into_strided_rows(dev):
+    """ops.linear / linear_bwd_data writing into the owned rows of a larger batch-strided buffer (how the
+    band model stages activations without a copy) == the plain call."""
+    b, n, k, m = 3, 700, 64, 128
+    x = wts.features((b, n, k), 51).bfloat16().to(dev)
+    w = wts.glorot(m, k, 52).bfloat16().to(dev)
+    bias = wts.small_bias(m, 53).to(dev)
+    big = torch.full((b, n + 40, m), 7.0, dtype=torch.bfloat16, device=dev)
+    view = big[:, 20:20 + n, :]
+    y = ops.linear(x, w, bias, relu=True, out=view)
+    assert y.data_ptr() == view.data_ptr()
+    assert torch.equal(view, ops.linear(x, w, bias, relu=True))
+    assert torch.all(big[:, :20] == 7.0) and torch.all(big[:, 20 + n:] == 7.0)       # nothing else touched
+    # strided INPUT as well
+    y2 = ops.linear(view, wts.glorot(k, m, 54).bfloat16().to(dev))
+    assert torch.equal(y2, ops.linear(view.contiguous(), wts.glorot(k, m, 54).bfloat16().to(dev)))
+    dy = wts.features((b, n, m), 55).bfloat16().to(dev)
+    gbig = torch.zeros((b, n + 8, k), dtype=torch.bfloat16, device=dev)
+    ops.linear_bwd_data(dy, w, out=gbig[:, 8:, :])
+    assert torch.equal(gbig[:, 8:, :], ops.linear_bwd_data(dy, w))
+    assert torch.all(gbig[:, :8] == 0)

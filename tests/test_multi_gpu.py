@@ -41,3 +41,20 @@ def test_band_model_two_gpus():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4 and out["loss_rel_err"] < 1e-5
+
+
+@pytest.mark.gpu
+def test_band_model_single_rank():
+    """The same check with ONE rank (runs on a single-GPU box): exercises the symmetric-memory
+    allocation, the peer-halo stencil kernel (halo warp, epoch protocol, boundary-rows-last order),
+    the in-place staging of BandGNNModel, the global loss shares and the gradient all-reduce."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    port = 29300 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tools", "band_model_check.py"), "--no-time"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4 and out["loss_rel_err"] < 1e-5
