@@ -205,6 +205,7 @@ def model_probes(dev):
         "edges_per_s": b * e1 * 6 / (ms * 1e-3),
         "flops_per_step": 2.0 * b * n * 1441792, "tflops": 2.0 * b * n * 1441792 / (ms * 1e-3) / 1e12}
     del x
+    model = model.float()          # config 5: bf16 activations, fp32 master weights (cast to bf16 per call)
     x1 = torch.randn(1, n, c, device=dev).to(torch.bfloat16)
     mask = (torch.arange(n, device=dev) % 125) == 124
 
@@ -214,8 +215,8 @@ def model_probes(dev):
     ms_t = timed(train_step, 2, 3)
     out["train_step_cfg5_member"] = {
         "workload": "cfg5 shape, one member: gwen_b200.train_step = forward + fused masked-L1 loss (target = input, "
-                    "mask id%125==124) + backward through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16, "
-                    "optimizer step excluded",
+                    "mask id%125==124) + backward through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16 activations, "
+                    "fp32 master weights and fp32 weight gradients, optimizer step excluded",
         "ms_per_member_step": ms_t, "member_steps_per_s": 1e3 / ms_t}
     gw.clear_graph_cache()
     return out

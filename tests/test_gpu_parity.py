@@ -805,3 +805,31 @@ def test_linear_into_strided_rows(dev):
     ops.linear_bwd_data(dy, w, out=gbig[:, 8:, :])
     assert torch.equal(gbig[:, 8:, :], ops.linear_bwd_data(dy, w))
     assert torch.all(gbig[:, :8] == 0)
+
+
+def test_mixed_precision_fp32_master_weights(dev):
+    """BASELINE config 5 runs bf16 activations with fp32 master weights: an fp32-parameter model fed
+    bf16 features computes exactly what the bf16-cast model computes (weights are rounded to bf16 per
+    call), and its parameter gradients come back in fp32."""
+    h, w, c, hid = 12, 11, 64, 128
+    ei = gw.grid(h, w, dev)
+    cfg = gw.GNNConfig(nodes_in=h * w, nodes_out=h * w, channels_in=c, channels_out=c, hidden_feats=hid)
+    torch.manual_seed(5)
+    master = gw.GNNModel(cfg).to(dev)                       # fp32 parameters
+    import copy
+    cast = copy.deepcopy(master).to(torch.bfloat16)
+    x = wts.features((2, h * w, c), 61).bfloat16().to(dev)
+    mask = (torch.arange(h * w, device=dev) % 3) == 1
+    y = master(x, ei)
+    assert y.dtype == torch.bfloat16 and torch.equal(y, cast(x, ei))
+    loss = gw.masked_l1_loss(y, x, mask)
+    loss.backward()
+    lc = gw.masked_l1_loss(cast(x, ei), x, mask)
+    lc.backward()
+    for (name, p), (_, q) in zip(master.named_parameters(), cast.named_parameters()):
+        if p.grad is None:
+            assert q.grad is None
+            continue
+        assert p.grad.dtype == torch.float32 and q.grad.dtype == torch.bfloat16
+        # same fp32 gradient, only the final cast differs
+        assert torch.equal(p.grad.to(torch.bfloat16), q.grad), name
