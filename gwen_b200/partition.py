@@ -414,12 +414,16 @@ class _BandGCNFn(torch.autograd.Function):
     def backward(ctx, dy):
         saved_in, weight, y = ctx.saved_tensors
         net, li, band = ctx.net, ctx.li, ctx.net.band
-        dz, db = ops.relu_bias_bwd(dy.contiguous(), y if ctx.relu else None, ctx.has_bias)
+        b = dy.shape[0]
+        gs = None
+        if not ctx.agg_first:   # dz is what gets aggregated: write it straight into its band buffer
+            gs = net.buffer(("b", li), b, weight.shape[0], dy.dtype)
+        dz, db = ops.relu_bias_bwd(dy, y if ctx.relu else None, ctx.has_bias,
+                                   out=None if gs is None else band.owned(gs))
         if db is not None:
             db = db.to(weight.dtype)
         need_dx = ctx.needs_input_grad[0]
         dx = None
-        b = dz.shape[0]
         if ctx.agg_first:
             dw = ops.linear_bwd_weight(dz, saved_in)                  # dW = dz^T (A_hat x)
             if need_dx:
@@ -427,7 +431,6 @@ class _BandGCNFn(torch.autograd.Function):
                 ops.linear_bwd_data(dz, weight, out=band.owned(gs))
                 dx = band.aggregate(gs)
         else:
-            gs = net.stage(("b", li), dz)
             dh = band.aggregate(gs)                                   # A_hat^T dz
             dw = ops.linear_bwd_weight(dh, saved_in)                  # dW = dh^T x
             if need_dx:
@@ -464,7 +467,7 @@ class BandGNNModel(torch.nn.Module):
         t = self.buffer(key, x.shape[0], x.shape[-1], x.dtype)
         own = self.band.owned(t)
         if not (x.data_ptr() == own.data_ptr() and x.stride() == own.stride()):
-            own.copy_(x)
+            ops.copy_rows_(own, x)
         return t
 
     def out_view(self, li: int, batch: int, feat: int, dtype):

@@ -833,3 +833,22 @@ def test_mixed_precision_fp32_master_weights(dev):
         assert p.grad.dtype == torch.float32 and q.grad.dtype == torch.bfloat16
         # same fp32 gradient, only the final cast differs
         assert torch.equal(p.grad.to(torch.bfloat16), q.grad), name
+
+
+def test_relu_bias_bwd_strided(dev):
+    """The fused mask + bias pass on batch-strided y / dy / out (band buffers) == the dense call."""
+    b, n, f = 3, 500, 128
+    y = wts.features((b, n, f), 71).bfloat16().to(dev)
+    dy = wts.features((b, n, f), 72).bfloat16().to(dev)
+    dz_ref, db_ref = ops.relu_bias_bwd(dy, y, True)
+    ybig = torch.zeros(b, n + 30, f, dtype=torch.bfloat16, device=dev)
+    ybig[:, 10:10 + n] = y
+    obig = torch.full((b, n + 16, f), 3.0, dtype=torch.bfloat16, device=dev)
+    dz, db = ops.relu_bias_bwd(dy, ybig[:, 10:10 + n], True, out=obig[:, 16:])
+    assert dz.data_ptr() == obig[:, 16:].data_ptr()
+    assert torch.equal(obig[:, 16:], dz_ref) and torch.all(obig[:, :16] == 3.0)
+    assert nmax(db, db_ref.double()) <= 1e-6
+    dz2, db2 = ops.relu_bias_bwd(dy, None, True, out=obig[:, 16:])          # no mask: copy + column sums
+    assert torch.equal(obig[:, 16:], dy) and nmax(db2, dy.double().sum((0, 1))) <= 1e-5
+    dz3, db3 = ops.relu_bias_bwd(dy, None, False)
+    assert dz3.data_ptr() == dy.data_ptr() and db3 is None

@@ -37,6 +37,7 @@ def timed(fn, warm, iters, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="kernel breakdown of one cfg 5 step on rank 0")
     ap.add_argument("--cfg5-batch", type=int, default=0,
                     help="also time the config 5 training step (1158 x 774, this many members) on the bands")
     args = ap.parse_args()
@@ -153,6 +154,15 @@ def main():
             net.loss(net(xo), xo, mo).backward()
             net.allreduce_grads()
         ms_t = timed(train, 1, 3, dev)
+        if args.profile and rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                train()
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=60), flush=True)
+        elif args.profile:
+            train()
+            torch.cuda.synchronize()
         res["cfg5_1158x774_B%d" % b] = {"train_step_ms": round(ms_t, 3), "member_steps_per_s": round(b * 1e3 / ms_t, 2),
                                           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
     if rank == 0:
