@@ -292,9 +292,13 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
   auto kern = k_grid_stencil<T, LPR>;
   GWEN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-  const int grid = std::min(a.num_tiles, std::max(1, sm_count() - sm_reserve()));
+  // experiment knobs (developer): consumer warps per CTA and CTAs per SM
+  static const int cw_env = env_int2("GWEN_STENCIL_CWARPS", 16, 2, 16);
+  static const int cps_env = env_int2("GWEN_STENCIL_CTAS_PER_SM", 1, 1, 4);
+  const int cps = a.peer ? 1 : cps_env;
+  const int grid = std::min(a.num_tiles, std::max(1, (sm_count() - sm_reserve()) * cps));
   // consumer sub-warps = TH * tw / SEG units when possible: 16 consumer warps + 1 producer warp
-  kern<<<grid, a.peer ? 576 : 544, smem, st>>>(xmap, a);
+  kern<<<grid, a.peer ? 576 : 32 * (cw_env + 1), smem, st>>>(xmap, a);
   GWEN_LAUNCH_CHECK("k_grid_stencil");
   return GWEN_OK;
 }
