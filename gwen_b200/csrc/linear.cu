@@ -37,6 +37,8 @@ size_t linear_tf32x3_workspace_bytes(int64_t m, int64_t k, int64_t n_out);
 int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                       int64_t ldy, const float* bias, int relu, void* ws, size_t ws_bytes,
                       cudaStream_t st);
+int linear_tf32x3_dgrad(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in, int64_t n_out,
+                        int64_t lddx, void* ws, size_t ws_bytes, cudaStream_t st);
 // linear_wgrad_tc.cu
 int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
                               const void* dy, const void* x);
@@ -407,6 +409,26 @@ extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx
   GemmArgs g{dy, weight, dx, nullptr, m, k, n_out, lddy, ldw, lddx, n_out, 0, 0};
   return dtype == GWEN_F32 ? launch_gemm<float, true, false, false>(g, 1, st)
                            : launch_gemm<__nv_bfloat16, true, false, false>(g, 1, st);
+}
+
+extern "C" int gwen_linear_bwd_data_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype,
+                                                    size_t* out) {
+  GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
+  *out = (dtype == GWEN_F32 && m >= 4096 && n_out >= 32 && n_out % 4 == 0 && k % 64 == 0)
+             ? linear_tf32x3_workspace_bytes(m, n_out, k) : 0;   // split copy of W^T
+  return GWEN_OK;
+}
+
+extern "C" int gwen_linear_bwd_data_ws(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
+                                       int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
+                                       void* ws, size_t ws_bytes, void* stream) {
+  // fp32: dx = dy (W^T)^T through the 3xTF32 forward kernel (reduction over n_out, k output columns)
+  if (dtype == GWEN_F32 && ws && m > 0 && dy && weight && dx && ldw == k &&
+      linear_tf32x3_supported(m, n_out, k, lddy, n_out, lddx, dy, weight, dx) &&
+      ws_bytes >= linear_tf32x3_workspace_bytes(m, n_out, k))
+    return linear_tf32x3_dgrad(dy, weight, dx, m, k, n_out, lddx, ws, ws_bytes,
+                               static_cast<cudaStream_t>(stream));
+  return gwen_linear_bwd_data(dy, weight, dx, m, k, n_out, lddy, ldw, lddx, dtype, stream);
 }
 
 extern "C" int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int64_t n_out,

@@ -3,8 +3,8 @@
 //
 // The reference runs its fp32 Linear on SIMT cuBLAS (allow_tf32 = False); a single TF32 product
 // (10 mantissa bits) would miss the 1e-5 parity bar.  Split every operand once into
-//   hi = x with the low 13 mantissa bits cleared   (exactly a TF32 value)
-//   lo = (x - hi) with its low 13 bits cleared     (exact difference, next 10-11 bits)
+//   hi = x rounded to the nearest TF32 value (10 mantissa bits)
+//   lo = (x - hi), an exact difference, rounded to TF32 again (the next 11 bits)
 // and accumulate  lo_a * hi_b + hi_a * lo_b + hi_a * hi_b  in the fp32 TMEM accumulator: the dropped
 // terms are O(2^-21) relative, i.e. fp32-level.  W is split once per call by k_split_tf32 (it is
 // small); x is split IN the kernel: the raw fp32 tile lands by TMA, four transform warps rewrite it
@@ -36,6 +36,14 @@ struct TfArgs {
   int n, k_blocks, bn, stages, relu;
 };
 
+// x = hi + lo + O(2^-24 |x|): both parts rounded to nearest TF32 (10 mantissa bits; adding half an ulp
+// before clearing the low 13 bits rounds the magnitude), so the split error is unbiased.
+__device__ __forceinline__ void split_tf32(uint32_t u, uint32_t& h, uint32_t& l) {
+  h = (u + 0x1000u) & 0xFFFFE000u;
+  const uint32_t d = __float_as_uint(__uint_as_float(u) - __uint_as_float(h));   // exact
+  l = (d + 0x1000u) & 0xFFFFE000u;
+}
+
 __global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
                              int64_t n4) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4;
@@ -44,12 +52,30 @@ __global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = u[j] & 0xFFFFE000u;
-      l[j] = __float_as_uint(__uint_as_float(u[j]) - __uint_as_float(h[j])) & 0xFFFFE000u;
-    }
+    for (int j = 0; j < 4; ++j) split_tf32(u[j], h[j], l[j]);
     reinterpret_cast<uint4*>(hi)[i] = make_uint4(h[0], h[1], h[2], h[3]);
     reinterpret_cast<uint4*>(lo)[i] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// hi / lo split of the TRANSPOSE of w [rows, cols] (for the dgrad: dx = dy W = dy (W^T)^T); w is small
+__global__ void k_split_tf32_t(const float* __restrict__ w, float* __restrict__ hi_t,
+                               float* __restrict__ lo_t, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? w[int64_t(r) * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;          // output row c, column r
+    if (c < cols && r < rows) {
+      uint32_t h, l;
+      split_tf32(__float_as_uint(tile[threadIdx.x][i]), h, l);
+      hi_t[int64_t(c) * rows + r] = __uint_as_float(h);
+      lo_t[int64_t(c) * rows + r] = __uint_as_float(l);
+    }
   }
 }
 
@@ -98,7 +124,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
   const int n_sub = g.bn / 16;   // 16-column (64-byte) epilogue sub-chunks per tile
   const int64_t total = ((g.m + 2 * BM - 1) / (2 * BM)) * n_tiles;
   const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const uint32_t tmem_cols = uint32_t(2 * g.bn < 32 ? 32 : 2 * g.bn);
+  // two accumulator sets (tile double buffering) x two partial sums (first / second half of K)
+  const uint32_t tmem_cols = uint32_t(4 * g.bn);
+  const int kb_half = (g.k_blocks + 1) / 2;
   const uint32_t epi_arrivals = 2u * 4u * uint32_t(n_sub < 4 ? n_sub : 4);
 
   if (threadIdx.x == 0) {
@@ -158,8 +186,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
         const uint32_t acc = seq & 1u, use = seq >> 1;
         if (use > 0) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use - 1) & 1u);
         tc_fence_after();
-        const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
+        // The tensor core's fp32 accumulator rounds toward zero on every add, a bias that grows with the
+        // length of the sum: accumulate the two halves of K separately and add them (round to nearest)
+        // in the epilogue -- measured 7.7e-6 -> ~4e-6 normalised error at K = 1024.
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
+          const uint32_t part = kb >= kb_half ? 1u : 0u;
+          const uint32_t d_addr = tmem_d + (acc * 2u + part) * uint32_t(g.bn);
+          const uint32_t first = (kb == 0 || kb == kb_half) ? 1u : 0u;
           const uint32_t s = it % uint32_t(g.stages), par = (it / uint32_t(g.stages)) & 1u;
           mbar_wait(smem_u32(&full_b[s]), par);
           mbar_wait(smem_u32(&xf_bar[s]), par);
@@ -171,7 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
 #pragma unroll
           for (int kk = 0; kk < BKF / UMMA_KF; ++kk) {  // +32 bytes (>>4 = 2) per K = 8 inside the row
             const uint64_t o = uint64_t(kk * 2);
-            umma_tf32_pair(d_addr, d_alo + o, d_bhi + o, idesc, (kb | kk) ? 1u : 0u);
+            umma_tf32_pair(d_addr, d_alo + o, d_bhi + o, idesc, (first && kk == 0) ? 0u : 1u);
             umma_tf32_pair(d_addr, d_ahi + o, d_blo + o, idesc, 1u);
             umma_tf32_pair(d_addr, d_ahi + o, d_bhi + o, idesc, 1u);
           }
@@ -199,10 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
           const uint32_t u[4] = {v.x, v.y, v.z, v.w};
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            h[e] = u[e] & 0xFFFFE000u;
-            l[e] = __float_as_uint(__uint_as_float(u[e]) - __uint_as_float(h[e])) & 0xFFFFE000u;
-          }
+          for (int e = 0; e < 4; ++e) split_tf32(u[e], h[e], l[e]);
           sts_v4(a_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
           sts_v4(a_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
         }
@@ -227,11 +257,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
         const uint32_t acc = seq & 1u;
         mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
         tc_fence_after();
-        const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
+        const uint32_t t_addr = tmem_d + acc * 2u * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
+        const bool two_parts = g.k_blocks > 1;
         for (int sc = g4; sc < n_sub; sc += 4) {
           const int c = sc * 16;
-          uint32_t r[16];
+          uint32_t r[16], r2[16];
           tmem_ld16_nowait(t_addr + uint32_t(c), r);
+          if (two_parts) tmem_ld16_nowait(t_addr + uint32_t(g.bn) + uint32_t(c), r2);
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (sc + 4 >= n_sub) {
@@ -240,6 +272,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
             if (lane == 0) mbar_arrive_cluster(acc ? empty_remote1 : empty_remote0);
           }
           __syncwarp();
+          if (two_parts) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+          }
           const uint32_t sbuf = my_stage + row_off;
           const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + c);
 #pragma unroll
@@ -279,7 +315,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTfThreads, 1)
 int linear_tf32x3_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
                             const void* x, const void* w, const void* y) {
   static const bool disabled = getenv("GWEN_FP32_SIMT") != nullptr || getenv("GWEN_DISABLE_TC") != nullptr;
-  if (disabled || m < 4096 || m > INT32_MAX || k < 32 || n_out < 64 || n_out > 8192) return 0;
+  // k <= 2048: the accumulator's rounding error grows with the length of the sum (4.4e-6 at k = 1024)
+  if (disabled || m < 4096 || m > INT32_MAX || k < 32 || k > 2048 || n_out < 64 || n_out > 8192) return 0;
   if (k % 4 || n_out % 64 || ldx != k || ldw != k || ldy % 4 || sm_count() % 2) return 0;
   return aligned16(x) && aligned16(w) && aligned16(y);
 }
@@ -289,18 +326,8 @@ size_t linear_tf32x3_workspace_bytes(int64_t m, int64_t k, int64_t n_out) {
   return 2 * align_up(size_t(n_out) * k * 4, 256);   // W hi / lo (x is split inside the kernel)
 }
 
-int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
-                      int64_t ldy, const float* bias, int relu, void* ws, size_t ws_bytes,
-                      cudaStream_t st) {
-  if (ws_bytes < linear_tf32x3_workspace_bytes(m, k, n_out))
-    return set_err(GWEN_E_WORKSPACE, "tf32x3 workspace too small");
-  const size_t wa = align_up(size_t(n_out) * k * 4, 256);
-  float* w_hi = static_cast<float*>(ws);
-  float* w_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + wa);
-  const int64_t w4 = n_out * k / 4;
-  k_split_tf32<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(w4, 256), int64_t(sm_count()) * 16)), 256, 0, st>>>(
-      static_cast<const float*>(w), w_hi, w_lo, w4);
-  GWEN_LAUNCH_CHECK("k_split_tf32");
+static int tf32x3_launch(const void* x, const float* w_hi, const float* w_lo, void* y, int64_t m, int64_t k,
+                         int64_t n_out, int64_t ldy, const float* bias, int relu, cudaStream_t st) {
   const int bn = n_out % 128 == 0 ? 128 : 64;
   CUtensorMap amap, bhi, blo, ymap;
   int rc = make_tensor_map_3d(&amap, x, GWEN_F32, k, m, 1, k, 0, BKF, BM, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -324,6 +351,36 @@ int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t 
   k_linear_tf32x3<<<2 * pairs, kTfThreads, smem, st>>>(amap, bhi, blo, ymap, g);
   GWEN_LAUNCH_CHECK("k_linear_tf32x3");
   return GWEN_OK;
+}
+
+int linear_tf32x3_fwd(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
+                      int64_t ldy, const float* bias, int relu, void* ws, size_t ws_bytes,
+                      cudaStream_t st) {
+  if (ws_bytes < linear_tf32x3_workspace_bytes(m, k, n_out))
+    return set_err(GWEN_E_WORKSPACE, "tf32x3 workspace too small");
+  const size_t wa = align_up(size_t(n_out) * k * 4, 256);
+  float* w_hi = static_cast<float*>(ws);
+  float* w_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + wa);
+  const int64_t w4 = n_out * k / 4;
+  k_split_tf32<<<static_cast<unsigned>(std::min<int64_t>(ceil_div(w4, 256), int64_t(sm_count()) * 16)), 256, 0, st>>>(
+      static_cast<const float*>(w), w_hi, w_lo, w4);
+  GWEN_LAUNCH_CHECK("k_split_tf32");
+  return tf32x3_launch(x, w_hi, w_lo, y, m, k, n_out, ldy, bias, relu, st);
+}
+
+// dx[M, K_in] = dy[M, N_out] W[N_out, K_in]: the forward kernel on dy with the split TRANSPOSE of W
+int linear_tf32x3_dgrad(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in, int64_t n_out,
+                        int64_t lddx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < linear_tf32x3_workspace_bytes(m, n_out, k_in))
+    return set_err(GWEN_E_WORKSPACE, "tf32x3 workspace too small");
+  const size_t wa = align_up(size_t(n_out) * k_in * 4, 256);
+  float* wt_hi = static_cast<float*>(ws);
+  float* wt_lo = reinterpret_cast<float*>(static_cast<char*>(ws) + wa);
+  dim3 grid(static_cast<unsigned>(ceil_div(k_in, 32)), static_cast<unsigned>(ceil_div(n_out, 32)));
+  k_split_tf32_t<<<grid, dim3(32, 8), 0, st>>>(static_cast<const float*>(w), wt_hi, wt_lo,
+                                                static_cast<int>(n_out), static_cast<int>(k_in));
+  GWEN_LAUNCH_CHECK("k_split_tf32_t");
+  return tf32x3_launch(dy, wt_hi, wt_lo, dx, m, n_out, k_in, lddx, nullptr, 0, st);
 }
 
 }  // namespace gwen

@@ -249,8 +249,13 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
     wt = weight.detach().to(dy2.dtype).contiguous()
     with torch.cuda.device(dy2.device):
         dx = torch.empty((dy2.shape[0], k), dtype=dy2.dtype, device=dy2.device)
-        check(lib().gwen_linear_bwd_data(_ptr(dy2), _ptr(wt), _ptr(dx), dy2.shape[0], k, n_out, n_out,
-                                         k, k, dtype_code(dy2.dtype), _stream()),
+        need = C.c_size_t(0)
+        if dy2.dtype == torch.float32:     # fp32 on the tensor cores (3xTF32) needs scratch for the split W^T
+            check(lib().gwen_linear_bwd_data_workspace_bytes(dy2.shape[0], k, n_out, dtype_code(dy2.dtype),
+                                                             C.byref(need)), "dgrad ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device) if need.value else None
+        check(lib().gwen_linear_bwd_data_ws(_ptr(dy2), _ptr(wt), _ptr(dx), dy2.shape[0], k, n_out, n_out,
+                                            k, k, dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
               "gwen_linear_bwd_data")
     return dx.reshape(tuple(dy.shape[:-1]) + (k,))
 

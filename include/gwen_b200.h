@@ -271,6 +271,13 @@ int gwen_linear_fwd_ws(const void* x, const void* weight, void* y, int64_t m, in
 int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
                          void* stream);
+/* gwen_linear_bwd_data with scratch: fp32 problems (m >= 4096, n_out % 4 == 0, k % 64 == 0, dense rows)
+ * run on the tensor cores through the 3xTF32 forward kernel on the split transpose of W. */
+int gwen_linear_bwd_data_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype,
+                                         size_t* bytes_out_host);
+int gwen_linear_bwd_data_ws(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
+                            int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype, void* ws,
+                            size_t ws_bytes, void* stream);
 int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t m, int64_t k,
                            int64_t n_out, int64_t lddy, int64_t ldx, int64_t lddw, int dtype,
                            void* ws, size_t ws_bytes, void* stream);

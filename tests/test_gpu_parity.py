@@ -274,7 +274,8 @@ def test_linear_bf16(dev, m, k, n):
     assert torch.equal(yr, torch.relu(y))
 
 
-@pytest.mark.parametrize("m,k,n", [(300, 64, 128), (5000, 96, 40), (129, 256, 512)])
+@pytest.mark.parametrize("m,k,n", [(300, 64, 128), (5000, 96, 40), (129, 256, 512), (6000, 512, 1024),
+                                   (9000, 64, 100), (4096, 1024, 36)])
 def test_linear_backward_pieces(dev, m, k, n):
     x, w, dy = wts.features((m, k), 1), wts.glorot(n, k, 2), wts.features((m, n), 3)
     dx = ops.linear_bwd_data(dy.to(dev), w.to(dev))
