@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1

@@ -46,6 +46,13 @@ int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out);
 int linear_tc_wgrad_bf16(const void* dy, const void* x, float* part, int64_t m, int64_t k_in,
                          int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st);
 
+// linear_wgrad_tf32x3.cu
+int linear_wgrad_tf32x3_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
+                                  const void* dy, const void* x);
+int linear_wgrad_tf32x3_splits(int64_t m, int64_t k_in, int64_t n_out);
+int linear_wgrad_tf32x3(const void* dy, const void* x, float* part, int64_t m, int64_t k_in, int64_t n_out,
+                        int64_t lddy, int64_t ldx, cudaStream_t st);
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
@@ -436,6 +443,7 @@ extern "C" int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int6
   GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
   int splits = wgrad_splits(m, k, n_out);
   if (k % 64 == 0 && n_out % 64 == 0 && m >= 256) splits = std::max(splits, linear_tc_wgrad_splits(m, k, n_out));
+  if (k % 4 == 0 && n_out % 4 == 0 && m >= 4096) splits = std::max(splits, linear_wgrad_tf32x3_splits(m, k, n_out));
   *out = static_cast<size_t>(splits) * n_out * k * sizeof(float) + 256;
   return GWEN_OK;
 }
@@ -460,6 +468,17 @@ extern "C" int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, 
     if (rc != GWEN_OK) return rc;
     k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(
         static_cast<const float*>(ws), tsplits, n_elems, n_elems, dw, lddw, k);
+    GWEN_LAUNCH_CHECK("k_reduce_splits");
+    return GWEN_OK;
+  }
+  if (dtype == GWEN_F32 && m > 0 && linear_wgrad_tf32x3_supported(m, k, n_out, lddy, ldx, dy, x)) {
+    const int fsplits = linear_wgrad_tf32x3_splits(m, k, n_out);
+    const size_t fneed = static_cast<size_t>(fsplits) * n_out * k * sizeof(float);
+    if (ws_bytes < fneed) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, fneed);
+    int rc = linear_wgrad_tf32x3(dy, x, static_cast<float*>(ws), m, k, n_out, lddy, ldx, st);
+    if (rc != GWEN_OK) return rc;
+    k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(
+        static_cast<const float*>(ws), fsplits, n_elems, n_elems, dw, lddw, k);
     GWEN_LAUNCH_CHECK("k_reduce_splits");
     return GWEN_OK;
   }
