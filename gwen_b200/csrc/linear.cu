@@ -30,6 +30,12 @@ int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t ld
 int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st);
 
+int linear_tc_batched_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                                int64_t x_bstride, int64_t y_bstride, const void* x, const void* w,
+                                const void* y, int b_mn);
+int linear_tc_batched_bf16(const void* x, const void* w, void* y, int64_t batch, int64_t m, int64_t k,
+                           int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int64_t x_bstride,
+                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st);
 // linear_tf32x3.cu
 int linear_tf32x3_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
                             const void* x, const void* w, const void* y);
@@ -416,6 +422,50 @@ extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx
   GemmArgs g{dy, weight, dx, nullptr, m, k, n_out, lddy, ldw, lddx, n_out, 0, 0};
   return dtype == GWEN_F32 ? launch_gemm<float, true, false, false>(g, 1, st)
                            : launch_gemm<__nv_bfloat16, true, false, false>(g, 1, st);
+}
+
+extern "C" int gwen_linear_batched_fwd(const void* x, const void* weight, void* y, int64_t batch, int64_t m,
+                                       int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                                       int64_t x_bstride, int64_t y_bstride, int dtype, const float* bias,
+                                       int epilogue, void* stream) {
+  GWEN_CHECK_ARG(batch >= 0 && m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (batch == 0 || m == 0 || n_out == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(x && weight && y, "null pointer");
+  if (dtype == GWEN_BF16 && batch > 1 &&
+      linear_tc_batched_supported(m, k, n_out, ldx, ldw, ldy, x_bstride, y_bstride, x, weight, y, 0))
+    return linear_tc_batched_bf16(x, weight, y, batch, m, k, n_out, ldx, ldw, ldy, x_bstride, y_bstride, bias,
+                                  (epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, static_cast<cudaStream_t>(stream));
+  const int64_t esz = dtype == GWEN_F32 ? 4 : 2;
+  for (int64_t b = 0; b < batch; ++b) {
+    int rc = gwen_linear_fwd(static_cast<const char*>(x) + b * x_bstride * esz, weight,
+                             static_cast<char*>(y) + b * y_bstride * esz, m, k, n_out, ldx, ldw, ldy, dtype,
+                             bias, epilogue, stream);
+    if (rc != GWEN_OK) return rc;
+  }
+  return GWEN_OK;
+}
+
+extern "C" int gwen_linear_batched_bwd_data(const void* dy, const void* weight, void* dx, int64_t batch,
+                                            int64_t m, int64_t k, int64_t n_out, int64_t lddy, int64_t ldw,
+                                            int64_t lddx, int64_t dy_bstride, int64_t dx_bstride, int dtype,
+                                            void* stream) {
+  GWEN_CHECK_ARG(batch >= 0 && m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  if (batch == 0 || m == 0 || k == 0) return GWEN_OK;
+  GWEN_CHECK_ARG(dy && weight && dx, "null pointer");
+  if (dtype == GWEN_BF16 && batch > 1 &&
+      linear_tc_batched_supported(m, n_out, k, lddy, ldw, lddx, dy_bstride, dx_bstride, dy, weight, dx, 1))
+    return linear_tc_batched_bf16(dy, weight, dx, batch, m, n_out, k, lddy, ldw, lddx, dy_bstride, dx_bstride,
+                                  nullptr, 0, 1, static_cast<cudaStream_t>(stream));
+  const int64_t esz = dtype == GWEN_F32 ? 4 : 2;
+  for (int64_t b = 0; b < batch; ++b) {
+    int rc = gwen_linear_bwd_data(static_cast<const char*>(dy) + b * dy_bstride * esz, weight,
+                                  static_cast<char*>(dx) + b * dx_bstride * esz, m, k, n_out, lddy, ldw, lddx,
+                                  dtype, stream);
+    if (rc != GWEN_OK) return rc;
+  }
+  return GWEN_OK;
 }
 
 extern "C" int gwen_linear_bwd_data_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype,

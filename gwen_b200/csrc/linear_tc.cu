@@ -29,7 +29,8 @@ using namespace tc;
 int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn);
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
-                        int b_mn, cudaStream_t st);
+                        int b_mn, cudaStream_t st, int64_t batch = 1, int64_t x_bstride = 0,
+                        int64_t y_bstride = 0);
 
 namespace {
 
@@ -417,6 +418,21 @@ int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t ld
 int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st) {
   return linear_tc3_fwd_bf16(dy, w, dx, m, n_out, k_in, lddy, ldw, lddx, nullptr, 0, 1, st);
+}
+
+// batch-strided forward / dgrad in ONE launch (bf16, CTA-pair kernel); 0 = not served
+int linear_tc_batched_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
+                                int64_t x_bstride, int64_t y_bstride, const void* x, const void* w,
+                                const void* y, int b_mn) {
+  if (x_bstride % 8 || y_bstride % 8) return 0;
+  if (!linear_tc_supported(m, k, n_out, ldx, ldw, ldy, x, w, y)) return 0;
+  return linear_tc3_supported(m, k, n_out, b_mn);
+}
+int linear_tc_batched_bf16(const void* x, const void* w, void* y, int64_t batch, int64_t m, int64_t k,
+                           int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int64_t x_bstride,
+                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st) {
+  return linear_tc3_fwd_bf16(x, w, y, m, k, n_out, ldx, ldw, ldy, bias, relu, b_mn, st, batch, x_bstride,
+                             y_bstride);
 }
 
 }  // namespace gwen

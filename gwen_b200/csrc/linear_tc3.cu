@@ -45,6 +45,7 @@ struct Tc3Args {
   int64_t m;
   int n, k_blocks, bn, stages, relu, bufs, row_major_tiles;
   int epi_groups;  // epilogue warp groups (of 4 warps) that work: 4, or 2 to trade staging for ring depth
+  int batch;  // independent [m, k] x-slices / [m, n] y-slices (third TMA coordinate), same W
   int b_mn;  // B operand is MN-major: w is [reduction][n] row-major (dgrad: dx = dy W)
 };
 
@@ -67,7 +68,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.n / g.bn;
   const int n_sub = g.bn / 32;  // 32-column epilogue sub-chunks per tile
-  const int64_t m_blocks = (g.m + 2 * BM - 1) / (2 * BM);
+  const int64_t mb_per_batch = (g.m + 2 * BM - 1) / (2 * BM);
+  const int64_t m_blocks = mb_per_batch * g.batch;   // row blocks of all batch slices
   const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   // Tile order.  row_major_tiles: a pair owns whole 256-row blocks (c, c + n_clusters, ..) and walks
   // their N tiles one after the other, so it completes full output rows within a few tiles (DRAM
@@ -122,7 +124,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
       for (int64_t idx = 0; idx < my_tiles; ++idx) {
         int mb, nt;
         tile_of(idx, mb, nt);
-        const int m0 = mb * (2 * BM) + int(rank) * BM;
+        const int bi = int(mb / mb_per_batch);
+        const int m0 = int(mb % mb_per_batch) * (2 * BM) + int(rank) * BM;
         const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
         for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
           const uint32_t s = it % uint32_t(g.stages), round = it / uint32_t(g.stages);
@@ -130,7 +133,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * stage_bytes);
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
           const uint32_t dst = base + s * stage_bytes;
-          tma_load_3d_pair(dst, &amap, kb * BK, m0, 0, bar);
+          tma_load_3d_pair(dst, &amap, kb * BK, m0, bi, bar);
           if (!g.b_mn) {
             tma_load_3d_pair(dst + a_bytes, &bmap, kb * BK, n0, 0, bar);
           } else {  // 64 (n) x 64 (reduction) boxes, one per 64 output columns, 8 KB apart
@@ -182,7 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
       for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
         int mb, nt;
         tile_of(idx, mb, nt);
-        const int m0 = mb * (2 * BM) + int(rank) * BM;
+        const int bi = int(mb / mb_per_batch);
+        const int m0 = int(mb % mb_per_batch) * (2 * BM) + int(rank) * BM;
         const int n0 = nt * g.bn;
         const uint32_t acc = seq & 1u;
         mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
@@ -220,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&ymap, my_stage + buf * 2048u, n0 + c, m0 + q * 32, 0);
+            tma_store_3d(&ymap, my_stage + buf * 2048u, n0 + c, m0 + q * 32, bi);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           buf = (buf + 1u) & uint32_t(g.bufs - 1);
@@ -249,18 +253,19 @@ int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn) {
 
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
-                        int b_mn, cudaStream_t st) {
+                        int b_mn, cudaStream_t st, int64_t batch, int64_t x_bstride, int64_t y_bstride) {
+  if (batch < 1 || batch > 65535) return set_err(GWEN_E_BADARG, "batch out of range");
   int bn = 0;
   for (int c : {256, 128, 64})
     if (n_out % c == 0) { bn = c; break; }
   if (!bn) return set_err(GWEN_E_NOSUPPORT, "tcgen05 pair GEMM needs n_out %% 64 == 0");
   CUtensorMap amap, bmap, ymap;
-  int rc = make_tensor_map_3d(&amap, x, GWEN_BF16, k, m, 1, ldx, 0, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = make_tensor_map_3d(&amap, x, GWEN_BF16, k, m, batch, ldx, x_bstride, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
   rc = b_mn ? make_tensor_map_3d(&bmap, w, GWEN_BF16, n_out, k, 1, ldw, 0, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B)
             : make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
-  rc = make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, 1, ldy, 0, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != GWEN_OK) return rc;
   const int k_blocks = static_cast<int>(ceil_div(k, BK));
   const size_t stage_bytes = size_t(BM + bn / 2) * BK * 2;
@@ -284,7 +289,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   if (stages < 2) return set_err(GWEN_E_NOSUPPORT, "tile does not fit in shared memory");
   // >= 120 KB keeps one CTA per SM (a pair owns up to all 512 TMEM columns of both SMs)
   const size_t smem = std::max<size_t>(stages * stage_bytes + staging_bytes + 1024, 120 * 1024);
-  const int64_t total = ceil_div(m, 2 * BM) * (n_out / bn);
+  const int64_t total = ceil_div(m, 2 * BM) * batch * (n_out / bn);
   const int pairs = static_cast<int>(std::min<int64_t>(total, std::max(1, (sm_count() - sm_reserve()) / 2)));
   static const int order_env = [] {
     const char* v = getenv("GWEN_TC3_ORDER");
@@ -292,7 +297,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   }();
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
-  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, b_mn};
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn};
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);

@@ -211,13 +211,14 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
             raise ValueError("out must be [..., N_out] with dense rows matching x")
         with torch.cuda.device(x.device):
             if xv.shape[0] == 1 or (xv.stride(0) == xv.shape[1] * k and ov.stride(0) == ov.shape[1] * n_out):
-                slices = [(xv, ov, xv.shape[0] * xv.shape[1])]
-            else:
-                slices = [(xv[b], ov[b], xv.shape[1]) for b in range(xv.shape[0])]
-            for xs, os_, m in slices:
-                check(lib().gwen_linear_fwd(_ptr(xs), _ptr(wt), _ptr(os_), m, k, n_out, k, k, n_out, code,
-                                            _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
-                      "gwen_linear_fwd")
+                check(lib().gwen_linear_fwd(_ptr(xv), _ptr(wt), _ptr(ov), xv.shape[0] * xv.shape[1], k, n_out, k,
+                                            k, n_out, code, _ptr(bias32), _lib.EPI_RELU if relu else 0,
+                                            _stream()), "gwen_linear_fwd")
+            else:       # batch-strided rows: one launch, the batch index is a TMA coordinate
+                check(lib().gwen_linear_batched_fwd(_ptr(xv), _ptr(wt), _ptr(ov), xv.shape[0], xv.shape[1], k,
+                                                    n_out, k, k, n_out, xv.stride(0), ov.stride(0), code,
+                                                    _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
+                      "gwen_linear_batched_fwd")
         return out
     x2 = x.reshape(-1, k).contiguous()
     with torch.cuda.device(x2.device):
@@ -241,9 +242,9 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
             raise ValueError("out must be [..., K] with dense rows matching dy")
         wt = weight.detach().to(dy.dtype).contiguous()
         with torch.cuda.device(dy.device):
-            for b in range(dv.shape[0]):
-                check(lib().gwen_linear_bwd_data(_ptr(dv[b]), _ptr(wt), _ptr(ov[b]), dv.shape[1], k, n_out, n_out,
-                                                 k, k, dtype_code(dy.dtype), _stream()), "gwen_linear_bwd_data")
+            check(lib().gwen_linear_batched_bwd_data(_ptr(dv), _ptr(wt), _ptr(ov), dv.shape[0], dv.shape[1], k,
+                                                     n_out, n_out, k, k, dv.stride(0), ov.stride(0),
+                                                     dtype_code(dy.dtype), _stream()), "gwen_linear_batched_bwd_data")
         return out
     dy2 = dy.reshape(-1, n_out).contiguous()
     wt = weight.detach().to(dy2.dtype).contiguous()

@@ -1,17 +1,25 @@
-"""Row-band mesh partition with a one-hop halo exchange per aggregation (multi-GPU path).
+"""Row-band mesh partition (multi-GPU path): one process per GPU, ensemble members in the outer batch.
 
 No reference counterpart: GWEN's GNN trainer spawns identical replicas (``models_gnn.py:341`` has
 DistributedDataParallel commented out).  BASELINE.json's north_star asks for the mesh to be
-spatially partitioned across the GPUs of one NVSwitch box; SURVEY.md section 8(e) fixes the
-scheme restated here:
+spatially partitioned across the GPUs of one NVSwitch box; SURVEY.md section 8(e) fixes the scheme:
+nodes are owned in contiguous id ranges (row bands of the H x W grid: node id = r*W + c) and a GCN
+layer needs one halo row from each neighbouring band.  Three implementations, fastest first:
 
-* nodes are owned in contiguous id ranges (row bands of the H x W grid: node id = r*W + c);
-* a rank's local graph is the slice of the GLOBAL destination-sorted CSR for its owned rows, so
-  message order and weights (global degrees) are exactly the single-GPU ones -> partitioned
-  results are bitwise equal to unpartitioned ones;
-* local source numbering is ``[owned | halo]`` with the halo sorted by global id; before an
-  aggregation the halo rows of its input are fetched from their owners with grouped
-  send/recv (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+* ``PeerMeshBand`` -- plain mesh graphs.  Feature buffers live in CUDA symmetric memory; the halo rows
+  are pulled from the neighbours' buffers over NVLink INSIDE the stencil aggregation kernel
+  (``gwen_grid_stencil_peer_fwd``: device-side epoch flags, boundary tile rows last).  One launch per
+  aggregation, no NCCL call.  ``BandGNNModel`` runs the six-layer model on it, forward and backward,
+  with the weight gradients all-reduced (``allreduce_grads``) and the reference's masked L1 loss split
+  into per-rank shares (``loss``).
+* ``MeshBand`` -- same layout, halos by grouped NCCL ``isend/irecv`` on a side stream under the
+  interior rows (gloo in the CPU tests), first / last owned rows in two extra launches.
+* ``partition_graph`` + ``HaloExchange`` + ``BandAggregator`` -- arbitrary graphs: a rank's local graph
+  is the slice of the GLOBAL destination-sorted CSR for its owned rows, so message order and weights
+  (global degrees) are exactly the single-GPU ones; local source numbering is ``[owned | halo]`` with
+  the halo sorted by global id and fetched with grouped send/recv before an aggregation.
+
+All three give results bitwise equal to the un-partitioned kernels.
 """
 from __future__ import annotations
 

@@ -271,6 +271,16 @@ int gwen_linear_fwd_ws(const void* x, const void* weight, void* y, int64_t m, in
 int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
                          void* stream);
+/* Batched forms: `batch` independent row blocks x[b] = x + b * x_bstride ([m, k], row pitch ldx) against the
+ * SAME weight, results to y[b] = y + b * y_bstride -- e.g. the owned rows of a band buffer per ensemble
+ * member.  bf16 problems the CTA-pair kernel takes run as ONE launch (the batch index is the third TMA
+ * coordinate); everything else is a loop over gwen_linear_fwd / gwen_linear_bwd_data. */
+int gwen_linear_batched_fwd(const void* x, const void* weight, void* y, int64_t batch, int64_t m, int64_t k,
+                            int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int64_t x_bstride,
+                            int64_t y_bstride, int dtype, const float* bias, int epilogue, void* stream);
+int gwen_linear_batched_bwd_data(const void* dy, const void* weight, void* dx, int64_t batch, int64_t m,
+                                 int64_t k, int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx,
+                                 int64_t dy_bstride, int64_t dx_bstride, int dtype, void* stream);
 /* gwen_linear_bwd_data with scratch: fp32 problems (m >= 4096, n_out % 4 == 0, k % 64 == 0, dense rows)
  * run on the tensor cores through the 3xTF32 forward kernel on the split transpose of W. */
 int gwen_linear_bwd_data_workspace_bytes(int64_t m, int64_t k, int64_t n_out, int dtype,
