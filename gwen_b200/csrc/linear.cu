@@ -245,6 +245,39 @@ __global__ void k_reduce_splits(const float* __restrict__ part, int splits, int6
   out[(i / cols) * ld_out + (i % cols)] = s;
 }
 
+// Partial-sum block for long reductions: block (x, g) sums splits [g * group, (g + 1) * group) of
+// `part` into tmp[g], so a reduction over thousands of partial rows (the bias gradient at COSMO-1E size:
+// ~3500 x feat) is two short fixed-order passes instead of `feat` threads looping over all of them.
+__global__ void k_reduce_groups(const float* __restrict__ part, int splits, int group, int64_t n_elems,
+                                float* __restrict__ tmp) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n_elems) return;
+  const int s0 = blockIdx.y * group, s1 = min(splits, s0 + group);
+  float s = 0.0f;
+  for (int k = s0; k < s1; ++k) s += part[int64_t(k) * n_elems + i];
+  tmp[int64_t(blockIdx.y) * n_elems + i] = s;
+}
+
+constexpr int kReduceGroup = 64;
+inline int64_t reduce_groups(int64_t splits) { return splits > 2 * kReduceGroup ? ceil_div(splits, kReduceGroup) : 0; }
+
+// out[i] = sum over splits of part[k][i], fixed order; `tmp` (reduce_groups(splits) x n_elems floats) is
+// used when the reduction is long.
+int reduce_vector(const float* part, int64_t splits, int64_t n_elems, float* out, float* tmp, cudaStream_t st) {
+  const int64_t groups = reduce_groups(splits);
+  const unsigned bx = static_cast<unsigned>(ceil_div(n_elems, 256));
+  if (groups > 0 && tmp) {
+    k_reduce_groups<<<dim3(bx, static_cast<unsigned>(groups)), 256, 0, st>>>(
+        part, static_cast<int>(splits), kReduceGroup, n_elems, tmp);
+    GWEN_LAUNCH_CHECK("k_reduce_groups");
+    k_reduce_splits<<<bx, 256, 0, st>>>(tmp, static_cast<int>(groups), n_elems, n_elems, out, n_elems, n_elems);
+  } else {
+    k_reduce_splits<<<bx, 256, 0, st>>>(part, static_cast<int>(splits), n_elems, n_elems, out, n_elems, n_elems);
+  }
+  GWEN_LAUNCH_CHECK("k_reduce_splits");
+  return GWEN_OK;
+}
+
 int wgrad_splits(int64_t m, int64_t k, int64_t n_out) {
   const int64_t tiles = ceil_div(n_out, BM) * ceil_div(k, BN);
   int64_t s = ceil_div(int64_t(sm_count()) * 2, tiles);
@@ -570,8 +603,8 @@ extern "C" int gwen_relu_bwd(const void* y, void* dy, int64_t rows, int64_t feat
 
 extern "C" int gwen_bias_grad_workspace_bytes(int64_t rows, int64_t feat, size_t* out) {
   GWEN_CHECK_ARG(out && rows >= 0 && feat >= 0, "bad arguments");
-  *out = static_cast<size_t>(std::max<int64_t>(1, ceil_div(rows, kFusedChunk))) * feat *
-             sizeof(float) + 256;
+  const int64_t chunks = std::max<int64_t>(1, ceil_div(rows, kFusedChunk));
+  *out = static_cast<size_t>(chunks + reduce_groups(chunks)) * feat * sizeof(float) + 256;
   return GWEN_OK;
 }
 
@@ -595,10 +628,8 @@ extern "C" int gwen_bias_grad(const void* dy, float* db, int64_t rows, int64_t f
     k_bias_partial<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
                                                         rows, feat, lddy, kBiasChunk, part);
   GWEN_LAUNCH_CHECK("k_bias_partial");
-  k_reduce_splits<<<static_cast<unsigned>(ceil_div(feat, 256)), 256, 0, st>>>(
-      part, static_cast<int>(chunks), feat, feat, db, feat, feat);
-  GWEN_LAUNCH_CHECK("k_reduce_splits");
-  return GWEN_OK;
+  float* tmp = ws_bytes >= size_t(chunks + reduce_groups(chunks)) * feat * sizeof(float) ? part + chunks * feat : nullptr;
+  return reduce_vector(part, chunks, feat, db, tmp, st);
 }
 
 extern "C" int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float* db, int64_t rows,
@@ -629,9 +660,8 @@ extern "C" int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float
         static_cast<__nv_bfloat16*>(dz), rows, static_cast<int>(groups), kFusedChunk, part);
   GWEN_LAUNCH_CHECK("k_relu_bias_bwd");
   if (db) {
-    k_reduce_splits<<<static_cast<unsigned>(ceil_div(feat, 256)), 256, 0, st>>>(
-        part, static_cast<int>(chunks), feat, feat, db, feat, feat);
-    GWEN_LAUNCH_CHECK("k_reduce_splits");
+    float* tmp = ws_bytes >= size_t(chunks + reduce_groups(chunks)) * feat * sizeof(float) ? part + chunks * feat : nullptr;
+    return reduce_vector(part, chunks, feat, db, tmp, st);
   }
   return GWEN_OK;
 }
