@@ -210,15 +210,25 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         if ov is None or ov.shape[:2] != xv.shape[:2] or ov.shape[2] != n_out or out.dtype != x.dtype:
             raise ValueError("out must be [..., N_out] with dense rows matching x")
         with torch.cuda.device(x.device):
-            if xv.shape[0] == 1 or (xv.stride(0) == xv.shape[1] * k and ov.stride(0) == ov.shape[1] * n_out):
-                check(lib().gwen_linear_fwd(_ptr(xv), _ptr(wt), _ptr(ov), xv.shape[0] * xv.shape[1], k, n_out, k,
-                                            k, n_out, code, _ptr(bias32), _lib.EPI_RELU if relu else 0,
-                                            _stream()), "gwen_linear_fwd")
-            else:       # batch-strided rows: one launch, the batch index is a TMA coordinate
+            dense = xv.shape[0] == 1 or (xv.stride(0) == xv.shape[1] * k and ov.stride(0) == ov.shape[1] * n_out)
+            epi = _lib.EPI_RELU if relu else 0
+            if x.dtype == torch.float32 or dense:
+                # fp32 goes through the workspace entry (3xTF32 on the tensor cores when it applies), one call
+                # per batch slice when the rows are batch-strided
+                slices = [(xv, ov, xv.shape[0] * xv.shape[1])] if dense else \
+                    [(xv[b], ov[b], xv.shape[1]) for b in range(xv.shape[0])]
+                for xs, os_, m in slices:
+                    need = C.c_size_t(0)
+                    if x.dtype == torch.float32:
+                        check(lib().gwen_linear_fwd_workspace_bytes(m, k, n_out, code, C.byref(need)), "linear ws")
+                    ws = torch.empty(need.value, dtype=torch.uint8, device=x.device) if need.value else None
+                    check(lib().gwen_linear_fwd_ws(_ptr(xs), _ptr(wt), _ptr(os_), m, k, n_out, k, k, n_out, code,
+                                                   _ptr(bias32), epi, _ptr(ws), need.value, _stream()),
+                          "gwen_linear_fwd")
+            else:       # bf16, batch-strided rows: one launch, the batch index is a TMA coordinate
                 check(lib().gwen_linear_batched_fwd(_ptr(xv), _ptr(wt), _ptr(ov), xv.shape[0], xv.shape[1], k,
                                                     n_out, k, k, n_out, xv.stride(0), ov.stride(0), code,
-                                                    _ptr(bias32), _lib.EPI_RELU if relu else 0, _stream()),
-                      "gwen_linear_batched_fwd")
+                                                    _ptr(bias32), epi, _stream()), "gwen_linear_batched_fwd")
         return out
     x2 = x.reshape(-1, k).contiguous()
     with torch.cuda.device(x2.device):
@@ -242,9 +252,20 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
             raise ValueError("out must be [..., K] with dense rows matching dy")
         wt = weight.detach().to(dy.dtype).contiguous()
         with torch.cuda.device(dy.device):
-            check(lib().gwen_linear_batched_bwd_data(_ptr(dv), _ptr(wt), _ptr(ov), dv.shape[0], dv.shape[1], k,
-                                                     n_out, n_out, k, k, dv.stride(0), ov.stride(0),
-                                                     dtype_code(dy.dtype), _stream()), "gwen_linear_batched_bwd_data")
+            if dy.dtype == torch.float32:     # workspace entry per slice (3xTF32 when it applies)
+                for b in range(dv.shape[0]):
+                    need = C.c_size_t(0)
+                    check(lib().gwen_linear_bwd_data_workspace_bytes(dv.shape[1], k, n_out, dtype_code(dy.dtype),
+                                                                     C.byref(need)), "dgrad ws")
+                    ws = torch.empty(need.value, dtype=torch.uint8, device=dy.device) if need.value else None
+                    check(lib().gwen_linear_bwd_data_ws(_ptr(dv[b]), _ptr(wt), _ptr(ov[b]), dv.shape[1], k, n_out,
+                                                        n_out, k, k, dtype_code(dy.dtype), _ptr(ws), need.value,
+                                                        _stream()), "gwen_linear_bwd_data")
+            else:
+                check(lib().gwen_linear_batched_bwd_data(_ptr(dv), _ptr(wt), _ptr(ov), dv.shape[0], dv.shape[1], k,
+                                                         n_out, n_out, k, k, dv.stride(0), ov.stride(0),
+                                                         dtype_code(dy.dtype), _stream()),
+                      "gwen_linear_batched_bwd_data")
         return out
     dy2 = dy.reshape(-1, n_out).contiguous()
     wt = weight.detach().to(dy2.dtype).contiguous()

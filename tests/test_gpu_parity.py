@@ -853,3 +853,60 @@ def test_relu_bias_bwd_strided(dev):
     assert torch.equal(obig[:, 16:], dy) and nmax(db2, dy.double().sum((0, 1))) <= 1e-5
     dz3, db3 = ops.relu_bias_bwd(dy, None, False)
     assert dz3.data_ptr() == dy.data_ptr() and db3 is None
+
+
+# ---------------------------------------------------------------------------------------------
+# red zones: kernels write exactly their output (compute-sanitizer is closed on this pool)
+# ---------------------------------------------------------------------------------------------
+def _guarded(shape, dtype, dev, pad=64):
+    """(view, check): an output view of `shape` inside a larger sentinel-filled buffer."""
+    n = 1
+    for s in shape:
+        n *= s
+    big = torch.full((n + 2 * pad,), 1234.0, dtype=dtype, device=dev)
+    view = big[pad:pad + n].view(shape)
+
+    def check():
+        assert torch.all(big[:pad] == 1234.0) and torch.all(big[pad + n:] == 1234.0), "wrote outside its output"
+    return view, check
+
+
+@pytest.mark.parametrize("hw", [(3, 5), (9, 33), (17, 23), (40, 70)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_red_zones_aggregation_and_fused(dev, hw, dt):
+    h, w = hw
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    for f in (64, 264):
+        x = wts.features((2, h * w, f), 81).to(dt).to(dev)
+        b = wts.small_bias(f, 82).to(dev)
+        for kern in ("rows", "tiled", "stencil"):
+            out, check = _guarded((2, h * w, f), dt, dev)
+            ops.aggregate(g, x, b, relu=True, kernel=kern, out=out)
+            torch.cuda.synchronize()
+            check()
+            assert nmax(out.float(), ops.aggregate(g, x, b, relu=True, kernel="rows").float()) <= (1e-6 if dt == torch.float32 else 2e-2)
+    if dt == torch.bfloat16:
+        x = wts.features((2, h * w, 128), 83).bfloat16().to(dev)
+        wt = wts.glorot(384, 128, 84).bfloat16().to(dev)
+        out, check = _guarded((2, h * w, 384), dt, dev)
+        ops.gcn_fused(g, x, wt, wts.small_bias(384, 85).to(dev), relu=True, out=out)
+        torch.cuda.synchronize()
+        check()
+
+
+@pytest.mark.parametrize("m,k,n", [(300, 64, 128), (257, 72, 96), (643, 1024, 64), (4100, 36, 64), (4500, 100, 128)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_red_zones_projections(dev, m, k, n, dt):
+    x = wts.features((m, k), 91).to(dt).to(dev)
+    wt = wts.glorot(n, k, 92).to(dt).to(dev)
+    dy = wts.features((m, n), 93).to(dt).to(dev)
+    out, check = _guarded((m, n), dt, dev)
+    ops.linear(x, wt, wts.small_bias(n, 94).to(dev), relu=True, out=out)
+    gout, gcheck = _guarded((m, k), dt, dev)
+    ops.linear_bwd_data(dy, wt, out=gout)
+    zout, zcheck = _guarded((m, n), dt, dev)
+    ops.relu_bias_bwd(dy, out.clone(), True, out=zout)
+    torch.cuda.synchronize()
+    check(), gcheck(), zcheck()
+    assert torch.equal(out, ops.linear(x, wt, wts.small_bias(n, 94).to(dev), relu=True))
+    assert torch.equal(gout, ops.linear_bwd_data(dy, wt))
