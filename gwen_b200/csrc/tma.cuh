@@ -5,6 +5,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gwen {
@@ -37,9 +39,15 @@ inline int make_tensor_map_3d(CUtensorMap* map, const void* base, int dtype, uin
   cuuint64_t strides[2] = {ld * esz, (batch > 1 ? bstride : ld * rows) * esz};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  static const CUtensorMapL2promotion promo = [] {   // developer knob: L2 promotion size of operand loads
+    const char* v = getenv("GWEN_TMA_PROMO");
+    return v && atoi(v) == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                               : (v && atoi(v) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                     : (v && atoi(v) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  }();
   CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_err(GWEN_E_CUDA,
                    "cuTensorMapEncodeTiled failed (%d): cols %llu rows %llu batch %llu ld %llu box "
