@@ -11,6 +11,7 @@ from .nn import GCNConv, gcn_conv
 from .models_gnn import (DownConvLayers, GCNConvLayers, GNNConfig, GNNModel, UpConvLayers,
                          loss_func)
 from . import ops  # noqa: F401
+from . import partition  # noqa: F401
 from .host_stream import HostPropagator
 from .train import masked_l1_loss, train_step
 from .data import GraphDataset
@@ -18,4 +19,4 @@ from .data import GraphDataset
 __version__ = "0.1.0"
 __all__ = ["GCNConv", "gcn_conv", "GraphCSR", "build_graph", "get_graph", "clear_graph_cache",
            "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "masked_l1_loss", "train_step", "GraphDataset", "GNNConfig",
-           "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops"]
+           "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops", "partition"]
