@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(576, 1)
   }
   __syncthreads();
   const int per_tile = static_cast<int>(a.batch) * a.slabs;
-  const int my_tiles = a.num_tiles > int(blockIdx.x)
-                           ? (a.num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
-  const int64_t n_items = int64_t(my_tiles) * per_tile;
+  // Work ITEMS (tile x batch x slab), not tiles, are dealt round-robin: 949 tiles over 148 CTAs would
+  // leave some CTAs 7 tiles and others 6 (9 % tail); 3796 items leave 26 vs 25.
+  const int64_t total_items = int64_t(a.num_tiles) * per_tile;
+  const int64_t n_items = total_items > int64_t(blockIdx.x)
+                              ? (total_items - 1 - int64_t(blockIdx.x)) / int64_t(gridDim.x) + 1 : 0;
   constexpr uint32_t kSlabBytes = LPR * 16u;                     // = a.slab_elems * sizeof(T)
   const uint32_t srow_bytes = uint32_t(a.tw + 2) * kSlabBytes;  // one staged mesh row
 
@@ -164,14 +166,15 @@ __global__ void __launch_bounds__(576, 1)
       uint32_t round = 0;
       bool halo_ready = !a.peer;
       for (int64_t it = 0; it < n_items; ++it) {
-        const int seq = int(blockIdx.x) + int(it / per_tile) * int(gridDim.x);
+        const int64_t gi = int64_t(blockIdx.x) + it * int64_t(gridDim.x);   // global item index
+        const int seq = int(gi / per_tile);
         const int t = tile_at(seq);
         if (!halo_ready && seq >= n_interior) {  // first tile that reads a halo row
           while (ld_acquire_gpu(a.ctl + CTL_HALO_DONE) < gridDim.x) __nanosleep(32);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores -> TMA reads
           halo_ready = true;
         }
-        const int rem = int(it % per_tile);
+        const int rem = int(gi % per_tile);
         const int b = rem / a.slabs, slab = rem % a.slabs;
         const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
         if (round > 0) mbar_wait(smem_u32(&empty_bar[st]), (round - 1) & 1u);
@@ -196,8 +199,9 @@ __global__ void __launch_bounds__(576, 1)
   int st = 0;
   uint32_t round = 0;
   for (int64_t it = 0; it < n_items; ++it) {
-    const int t = tile_at(int(blockIdx.x) + int(it / per_tile) * int(gridDim.x));
-    const int rem = int(it % per_tile);
+    const int64_t gi = int64_t(blockIdx.x) + it * int64_t(gridDim.x);
+    const int t = tile_at(int(gi / per_tile));
+    const int rem = int(gi % per_tile);
     const int b = rem / a.slabs, slab = rem % a.slabs;
     const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
     const int rows_valid = min(TH, a.hd - r0), cols_valid = min(a.tw, a.w - c0);
@@ -296,7 +300,8 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
   static const int cw_env = env_int2("GWEN_STENCIL_CWARPS", 16, 2, 16);
   static const int cps_env = env_int2("GWEN_STENCIL_CTAS_PER_SM", 1, 1, 4);
   const int cps = a.peer ? 1 : cps_env;
-  const int grid = std::min(a.num_tiles, std::max(1, (sm_count() - sm_reserve()) * cps));
+  const int64_t items = int64_t(a.num_tiles) * a.batch * a.slabs;
+  const int grid = static_cast<int>(std::min<int64_t>(items, std::max(1, (sm_count() - sm_reserve()) * cps)));
   // consumer sub-warps = TH * tw / SEG units when possible: 16 consumer warps + 1 producer warp
   kern<<<grid, a.peer ? 576 : 32 * (cw_env + 1), smem, st>>>(xmap, a);
   GWEN_LAUNCH_CHECK("k_grid_stencil");
