@@ -102,24 +102,38 @@ __global__ void __launch_bounds__(576, 1)
   }
   __syncthreads();
   const int per_tile = static_cast<int>(a.batch) * a.slabs;
-  // Work ITEMS (tile x batch x slab), not tiles, are dealt round-robin: 949 tiles over 148 CTAs would
-  // leave some CTAs 7 tiles and others 6 (9 % tail); 3796 items leave 26 vs 25.
+  // Work ITEMS (batch x tile x slab), not tiles, are dealt round-robin: 949 tiles over 148 CTAs would
+  // leave some CTAs 7 tiles and others 6 (9 % tail); 3796 items leave 26 vs 25.  Item order: batch
+  // slowest, then tile, slab fastest -- CTAs that run together fetch all slabs of ~37 neighbouring tiles
+  // of ONE member: whole rows at a time from DRAM, and the halos of vertical neighbours (25 tiles later)
+  // are still in L2.
   const int64_t total_items = int64_t(a.num_tiles) * per_tile;
   const int64_t n_items = total_items > int64_t(blockIdx.x)
                               ? (total_items - 1 - int64_t(blockIdx.x)) / int64_t(gridDim.x) + 1 : 0;
   constexpr uint32_t kSlabBytes = LPR * 16u;                     // = a.slab_elems * sizeof(T)
   const uint32_t srow_bytes = uint32_t(a.tw + 2) * kSlabBytes;  // one staged mesh row
 
-  // Peer mode walks the interior tile rows first and the two tile rows that read a halo row last
-  // (tile row 0, then the bottom one), so the halo fetch runs under the interior work.
+  // Peer mode walks the interior tile rows (of all members) first and the two tile rows that read a halo
+  // row last (tile row 0, then the bottom one), so the halo fetch runs under the interior work.
   const int tiles_y = a.num_tiles / a.tiles_x;
-  const int n_interior = tiles_y > 2 ? (tiles_y - 2) * a.tiles_x : 0;
-  auto tile_at = [&](int seq) {
-    if (!a.peer) return seq;
-    if (seq < n_interior) return seq + a.tiles_x;
-    const int r = seq - n_interior;              // boundary tiles
-    if (r < a.tiles_x) return r;                 // tile row 0
-    return (tiles_y - 1) * a.tiles_x + (r - a.tiles_x);
+  const int n_interior = a.peer ? (tiles_y > 2 ? (tiles_y - 2) * a.tiles_x : 0) : a.num_tiles;
+  const int64_t n_int_items = int64_t(a.batch) * n_interior * a.slabs;
+  auto decode = [&](int64_t gi, int& b, int& t, int& slab) {
+    if (gi < n_int_items) {
+      const int64_t per_b = int64_t(n_interior) * a.slabs;
+      b = int(gi / per_b);
+      const int r = int(gi % per_b);
+      slab = r % a.slabs;
+      t = r / a.slabs + (a.peer ? a.tiles_x : 0);
+    } else {                                       // boundary tiles (peer mode only)
+      const int nb = a.num_tiles - n_interior;
+      const int64_t g2 = gi - n_int_items, per_b = int64_t(nb) * a.slabs;
+      b = int(g2 / per_b);
+      const int r = int(g2 % per_b);
+      slab = r % a.slabs;
+      const int q = r / a.slabs;
+      t = q < a.tiles_x ? q : (tiles_y - 1) * a.tiles_x + (q - a.tiles_x);
+    }
   };
 
   if (warp == ncw + 1) {
@@ -167,15 +181,13 @@ __global__ void __launch_bounds__(576, 1)
       bool halo_ready = !a.peer;
       for (int64_t it = 0; it < n_items; ++it) {
         const int64_t gi = int64_t(blockIdx.x) + it * int64_t(gridDim.x);   // global item index
-        const int seq = int(gi / per_tile);
-        const int t = tile_at(seq);
-        if (!halo_ready && seq >= n_interior) {  // first tile that reads a halo row
+        int b, t, slab;
+        decode(gi, b, t, slab);
+        if (!halo_ready && gi >= n_int_items) {  // first tile that reads a halo row
           while (ld_acquire_gpu(a.ctl + CTL_HALO_DONE) < gridDim.x) __nanosleep(32);
           asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores -> TMA reads
           halo_ready = true;
         }
-        const int rem = int(gi % per_tile);
-        const int b = rem / a.slabs, slab = rem % a.slabs;
         const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
         if (round > 0) mbar_wait(smem_u32(&empty_bar[st]), (round - 1) & 1u);
         const uint32_t bar = smem_u32(&full_bar[st]);
@@ -200,9 +212,8 @@ __global__ void __launch_bounds__(576, 1)
   uint32_t round = 0;
   for (int64_t it = 0; it < n_items; ++it) {
     const int64_t gi = int64_t(blockIdx.x) + it * int64_t(gridDim.x);
-    const int t = tile_at(int(gi / per_tile));
-    const int rem = int(gi % per_tile);
-    const int b = rem / a.slabs, slab = rem % a.slabs;
+    int b, t, slab;
+    decode(gi, b, t, slab);
     const int r0 = (t / a.tiles_x) * TH, c0 = (t % a.tiles_x) * a.tw;
     const int rows_valid = min(TH, a.hd - r0), cols_valid = min(a.tw, a.w - c0);
     const int64_t col = int64_t(slab) * a.slab_elems + int64_t(l) * VN;
