@@ -6,14 +6,15 @@ everything on the device.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional
+from typing import List, Optional, Tuple
 
 import torch
+import torch.distributed as dist
 
 from ._lib import check, lib
 from .ops import dtype_code
 
-__all__ = ["masked_l1_loss", "train_step"]
+__all__ = ["masked_l1_loss", "train_step", "eval_step", "gather_eval_results"]
 
 
 class _MaskedL1(torch.autograd.Function):
@@ -78,3 +79,31 @@ def train_step(model, node_features: torch.Tensor, edge_index, target_mask: torc
     if scheduler is not None:
         scheduler.step()
     return loss.detach()
+
+
+@torch.no_grad()
+def eval_step(model, node_features: torch.Tensor, edge_index, target_mask: torch.Tensor
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One iteration of the reference evaluation loop (``models_gnn.py:440-450``): forward, the masked L1
+    loss against the input features, and the prediction the reference keeps, ``output[1]``.  Device
+    scalars / tensors, no host synchronisation."""
+    output = model(node_features, edge_index)
+    return masked_l1_loss(output, node_features, target_mask), output[1]
+
+
+def gather_eval_results(avg_loss: torch.Tensor, y_preds: List[torch.Tensor], group=None
+                        ) -> Optional[Tuple[float, torch.Tensor]]:
+    """The collective tail of ``eval_gnn_with_configs`` (``models_gnn.py:452-489``): every rank
+    contributes its average loss and its list of kept predictions; rank 0 returns
+    ``(mean of the ranks' losses, predictions concatenated in rank order)``, the other ranks ``None``.
+    The reference all_gathers the rank ids next to the predictions and sorts by them; ``all_gather``
+    already returns rank order, so the sort is the identity and is not repeated here."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    y = torch.cat([p.reshape(1, -1) if p.dim() == 1 else p for p in y_preds]) if y_preds else avg_loss.new_zeros(0)
+    ys = [torch.zeros_like(y) for _ in range(world)]
+    dist.all_gather(ys, y.contiguous(), group=group)
+    losses = [torch.zeros_like(avg_loss) for _ in range(world)]
+    dist.all_gather(losses, avg_loss.detach().contiguous(), group=group)
+    if rank != 0:
+        return None
+    return float(torch.stack(losses).mean()), torch.cat(ys).cpu()

@@ -910,3 +910,23 @@ def test_red_zones_projections(dev, m, k, n, dt):
     check(), gcheck(), zcheck()
     assert torch.equal(out, ops.linear(x, wt, wts.small_bias(n, 94).to(dev), relu=True))
     assert torch.equal(gout, ops.linear_bwd_data(dy, wt))
+
+
+def test_eval_step_matches_oracle(dev):
+    """eval_step (reference eval loop body, models_gnn.py:440-450): loss vs the oracle model + loss_func on
+    the CPU, and the kept prediction output[1]."""
+    ei, n, c, hid = orc.complete_graph(7), 7, 12, 64
+    ref = orc.GNNModelOracle(c, c, hid)
+    wts.fill_model_(ref, 9)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    model = gw.GNNModel(cfg)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev).eval()
+    x = wts.features((n, c), 10)
+    mask = torch.tensor([0, 1, 0, 1, 1, 0, 0], dtype=torch.bool)
+    with torch.no_grad():
+        yr = ref(x, ei)
+        lr = orc.loss_func(yr, x, mask)
+    loss, kept = gw.eval_step(model, x.to(dev), ei.to(dev), mask.to(dev))
+    assert abs(loss.item() - lr.item()) <= 1e-5 * abs(lr.item())
+    assert nmax(kept, yr[1]) <= FP32_TOL and not loss.requires_grad

@@ -129,3 +129,30 @@ def _band_worker(rank, world, port, h, w, f, batch):
 def test_mesh_band_exchange_gloo(world, batch):
     port = 31500 + (os.getpid() % 2000) + world * 5 + batch
     mp.spawn(_band_worker, args=(world, port, 9, 6, 4, batch), nprocs=world, join=True)
+
+
+def _eval_gather_worker(rank, world, port):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gwen_b200.train import gather_eval_results
+    # two kept predictions per rank (output[1] of two samples), a rank-dependent loss
+    preds = [torch.full((5,), float(10 * rank + i)) for i in range(2)]
+    res = gather_eval_results(torch.tensor(float(rank + 1)), preds)
+    if rank == 0:
+        loss, y = res
+        assert abs(loss - sum(range(1, world + 1)) / world) < 1e-6
+        want = torch.cat([torch.full((1, 5), float(10 * r + i)) for r in range(world) for i in range(2)])
+        assert torch.equal(y, want)
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_eval_results_gloo(world):
+    """Collective tail of the reference eval loop (models_gnn.py:452-489): losses averaged over the
+    ranks, predictions concatenated in rank order, only rank 0 gets the result."""
+    port = 29700 + (os.getpid() % 1500) + world
+    mp.spawn(_eval_gather_worker, args=(world, port), nprocs=world, join=True)
