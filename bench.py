@@ -14,11 +14,23 @@ N > 1 (launched with torch.distributed.run, one rank per GPU): WEAK scaling -- e
 582 x 390 row band of a (582 N) x 390 mesh.  The one-row halos are fetched INSIDE the aggregation
 kernel from the neighbours' buffers over NVLink peer memory (gwen_grid_stencil_peer_fwd,
 partition.PeerMeshBand); --halo nccl selects the NCCL send/recv exchange (partition.MeshBand).
+Before anything is timed every rank checks its band of the partitioned result BITWISE against the
+single-GPU stencil on the same global input (``partition_parity``).
 
 Timing: W untimed steps, then exactly K steps bracketed by barrier + synchronize, CUDA events on
-the launching stream, max over ranks.  Inputs + outputs (465 MB) exceed the 126 MB L2, so no
-explicit flush is needed.  ``e2e`` repeats the measurement through the public layer API with
-pinned HOST buffers (H2D of x and D2H of the result inside the timed region).
+the launching stream, max over ranks.  The step rotates over three input/output buffer pairs
+(1.4 GB per rank >> 126 MB L2): no line of a step's input or output survives in L2 until the
+buffer comes round again.  When K < 200 a second region of 200 steps is timed as well
+(``long_run``); the roofline uses the longer region.  ``e2e`` repeats the measurement through the
+public API with pinned HOST buffers (H2D of x and D2H of the result inside the timed region).
+
+``other_configs`` carries BASELINE's remaining configs, measured in the same invocation:
+  N = 1: cfg 3 full six-layer forward (bf16, B = 8) next to the torch-op sequence torch_geometric 2.3.1
+         runs for the same layers on the same GPU (``gpu_reference``) and an in-run parity check of a row
+         band against the fp32 oracle; one cfg 5 member training step; cfg 4 (2048^2) forward and
+         forward+backward on one GPU (the N = 1 point of the strong-scaling family).
+  N > 1: cfg 4 strong scaling (the same fixed 2048^2 mesh split into row bands: forward, and
+         forward + backward + gradient all-reduce); at N >= 4 the cfg 5 training step (B = 21).
 """
 from __future__ import annotations
 
@@ -35,9 +47,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 H, W, FEAT = 582, 390, 256
+NBUF = 3
+LONG_STEPS = 200
 METRIC, UNIT = "gcn_message_passing_edges_per_s", "edges/s"
 WORKLOAD = ("cfg2: synthetic COSMO-2E grid 582x390 (226980 nodes, E'=2036992 messages incl. self "
             "loops), F=256 fp32, single-layer message+aggregate (GCNConv.propagate)")
+BF16_TOL = 2e-2
 
 
 def parse():
@@ -49,27 +64,20 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-model-probes", action="store_true",
-                    help="skip the cfg3 full-forward / cfg5 member-step context numbers (N = 1)")
+                    help="skip other_configs (cfg 3 forward / cfg 4 strong scaling / cfg 5 training step)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="N > 1: halo exchange inside the kernel over peer memory, or NCCL send/recv")
     return ap.parse_args()
 
 
-def measured_peak():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+            j = json.load(f)
+        return (float(j["hbm_gbs"]), float(j.get("bf16_tflops_sustained", 1407.0)),
+                "measured (MEASURED_PEAKS.json: hbm_gbs copy peak, bf16_tflops_sustained)")
     except Exception:  # noqa: BLE001
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "k_grid_stencil_cfg2.json")) as f:
-            return json.load(f).get("dram_bytes_per_launch")
-    except Exception:  # noqa: BLE001
-        return None
+        return 6650.0, 1407.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 class ClockSampler:
@@ -166,60 +174,315 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-# context numbers for the other BASELINE configs (N = 1 only, a few seconds): the full six-layer
-# GNNModel forward at config 3 and one forward+backward member step at the config 5 shape
+# "reference torch_geometric GPU path": the op sequence PyG 2.3.1 executes for GCNConv (SURVEY.md table
+# 2.3: add_remaining_self_loops + gcn_norm per call, F.linear, index_select, multiply, scatter_add_,
+# + bias, relu), restated with the same ATen ops on the GPU.  Baseline leg only: nothing of ours runs in it.
 # ---------------------------------------------------------------------------------------------
-def model_probes(dev):
+def torch_gcn_norm(edge_index, n, dtype):
+    import torch
+    row, col = edge_index[0], edge_index[1]
+    keep = row != col
+    loop = torch.arange(n, device=edge_index.device)
+    ei = torch.cat([edge_index[:, keep], torch.stack([loop, loop])], dim=1)
+    ew = torch.ones(ei.size(1), dtype=dtype, device=ei.device)
+    deg = torch.zeros(n, dtype=dtype, device=ei.device).scatter_add_(0, ei[1], ew)
+    dis = deg.pow(-0.5)
+    dis.masked_fill_(dis == float("inf"), 0)
+    return ei, dis[ei[0]] * ew * dis[ei[1]]
+
+
+def torch_gcn_conv(x, edge_index, weight, bias, relu, cache=None):
+    import torch
+    n = x.size(-2)
+    ei, ew = cache if cache is not None else torch_gcn_norm(edge_index, n, x.dtype)
+    h = torch.nn.functional.linear(x, weight)
+    msg = h.index_select(-2, ei[0]) * ew.view(-1, 1)
+    out = torch.zeros_like(h).scatter_add_(-2, ei[1].view(-1, 1).expand_as(msg), msg)
+    out = out + bias
+    return torch.relu(out) if relu else out
+
+
+def _timed(fn, warm, iters):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def _live_layers(model):
+    d, u = model.conv_layers.down_conv_layers, model.conv_layers.up_conv_layers
+    return (("conv1", d.conv1, True), ("conv2", d.conv2, True), ("conv3", d.conv3, True),
+            ("upconv3", u.upconv3, True), ("upconv4", u.upconv4, True), ("upconv5", u.upconv5, False))
+
+
+# ---------------------------------------------------------------------------------------------
+# other_configs, N = 1
+# ---------------------------------------------------------------------------------------------
+def probe_full_forward_cfg3(dev):
+    """BASELINE config 3: COSMO-1E grid, six layers, bf16, B = 8.  Ours, the PyG op sequence on the same
+    GPU, and an in-run parity check of one member's row band against the fp32 oracle."""
     import torch
     import gwen_b200 as gw
+    _, tf_peak, _ = measured_peaks()
     h, wd, c, b = 1158, 774, 64, 8
     n = h * wd
-    out = {}
+    torch.manual_seed(23)
+    ei = gw.grid(h, wd, dev)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
+    model32 = gw.GNNModel(cfg)                       # fp32 master copy (CPU) for the oracle
+    with torch.no_grad():
+        for p in model32.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)                    # exercise the bias path (PyG inits biases to 0)
+    model = gw.GNNModel(cfg)
+    model.load_state_dict(model32.state_dict())
+    model = model.to(dev).to(torch.bfloat16)
+    xg = torch.Generator().manual_seed(23)
+    x_cpu = torch.randn(b, n, c, generator=xg)
+    x = x_cpu.to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ms = _timed(lambda: model(x, ei), 2, 5)
+        y = model(x, ei)
+    e1 = gw.grid_edge_count(h, wd)
+    flops = 2.0 * b * n * 1441792
+    out = {
+        "workload": "cfg3: COSMO-1E grid 1158x774 (896292 nodes, E'=%d), six GCN layers 64-1024-512-256-512-1024-64, bf16, "
+                    "8 ensemble members per step, synthetic data, random-init weights" % e1,
+        "ms_per_step": ms, "grid_steps_per_s": 1e3 / ms, "member_steps_per_s": b * 1e3 / ms,
+        "edges_per_s": b * e1 * 6 / (ms * 1e-3), "flops_per_step": flops, "tflops": flops / (ms * 1e-3) / 1e12,
+        "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                     "frac": flops / (ms * 1e-3) / 1e12 / tf_peak,
+                     "note": "whole forward; lower bounds: %.1f ms (flops at the sustained bf16 peak), 14.9 ms "
+                             "(97 GB of unfused activation traffic at the copy peak)" % (flops / tf_peak / 1e9)}}
+    # ---- in-run parity: member 0, rows [600, 608) vs the fp32 oracle on the 20-row band [594, 614) ----
+    try:
+        from oracle import gcn_oracle as orc  # checker only
+        ref = orc.GNNModelOracle(c, c, 1024)
+        ref.load_state_dict(model32.state_dict())
+        r0, r1, halo = 600, 608, 6
+        with torch.no_grad():
+            band = x_cpu[0, (r0 - halo) * wd:(r1 + halo) * wd]
+            yr = ref(band, orc.grid(r1 - r0 + 2 * halo, wd))[halo * wd:(halo + r1 - r0) * wd]
+        yo = y[0, r0 * wd:r1 * wd].float().cpu()
+        nmax = ((yo - yr).abs().max() / yr.abs().max()).item()
+        out["parity"] = {"nmax_vs_fp32_oracle_band": nmax, "tol": BF16_TOL, "ok": bool(nmax <= BF16_TOL),
+                         "what": "member 0, mesh rows 600..607 (6192 nodes x 64 channels) of the bf16 forward vs the "
+                                 "fp32 CPU oracle evaluated on the 20-row band 594..613 (six layers reach six rows); "
+                                 "max|y - y_ref| / max|y_ref|"}
+    except Exception as e:  # noqa: BLE001
+        out["parity"] = {"error": str(e)[:200]}
+    # ---- the PyG op sequence on this GPU, one member at a time (its [E', 1024] message tensor is 16.5 GB) ----
+    try:
+        layers = _live_layers(model)
+
+        def torch_forward(xm, cached):
+            cache = torch_gcn_norm(ei, n, xm.dtype) if cached else None
+            for _, conv, relu in layers:
+                xm = torch_gcn_conv(xm, ei, conv.lin.weight, conv.bias, relu, cache)
+            return xm
+        with torch.no_grad():
+            ms_re = _timed(lambda: torch_forward(x[0], False), 1, 3) * b
+            ms_ca = _timed(lambda: torch_forward(x[0], True), 1, 3) * b
+            yt = torch_forward(x[0], True)
+        out["gpu_reference"] = {
+            "what": "torch op sequence of torch_geometric 2.3.1 GCNConv (gcn_norm, F.linear, index_select, mul, "
+                    "scatter_add_, +bias, relu) on the same GPU, bf16, one member at a time x %d" % b,
+            "ms": ms_re, "norm": "recomputed", "speedup": ms_re / ms,
+            "ms_norm_cached": ms_ca, "speedup_norm_cached": ms_ca / ms,
+            "nmax_ours_vs_torch_bf16_sequence": ((y[0].float() - yt.float()).abs().max() / yt.float().abs().max()).item(),
+            "note": "the torch sequence rounds every intermediate to bf16 and adds in atomics order, so the "
+                    "comparison with it is not a parity statement; parity is the fp32-oracle band above"}
+        del yt
+    except Exception as e:  # noqa: BLE001
+        out["gpu_reference"] = {"error": str(e)[:200]}
+    del x, y, model
+    gw.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
+def probe_train_member_cfg5(dev):
+    import torch
+    import gwen_b200 as gw
+    h, wd, c = 1158, 774, 64
+    n = h * wd
+    torch.manual_seed(23)
+    ei = gw.grid(h, wd, dev)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
+    model = gw.GNNModel(cfg).to(dev)          # bf16 activations, fp32 master weights (cast once per weight version)
+    x1 = torch.randn(1, n, c, device=dev).to(torch.bfloat16)
+    mask = (torch.arange(n, device=dev) % 125) == 124
+    ms_t = _timed(lambda: gw.train_step(model, x1, ei, mask), 2, 3)
+    del model, x1
+    gw.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return {"workload": "cfg5 shape, one member: gwen_b200.train_step = forward + fused masked-L1 loss (target = input, "
+                        "mask id%125==124) + backward through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16 "
+                        "activations, fp32 master weights and fp32 weight gradients, optimizer step excluded",
+            "ms_per_member_step": ms_t, "member_steps_per_s": 1e3 / ms_t}
+
+
+def probe_cfg4_single(dev):
+    """The N = 1 point of BASELINE config 4's strong-scaling family: the un-partitioned model on the whole
+    2048 x 2048 mesh (B = 1, bf16)."""
+    import torch
+    import gwen_b200 as gw
+    h = wd = 2048
+    n, c = h * wd, 64
     torch.manual_seed(23)
     ei = gw.grid(h, wd, dev)
     cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
     model = gw.GNNModel(cfg).to(dev).to(torch.bfloat16)
-    x = torch.randn(b, n, c, device=dev).to(torch.bfloat16)
-
-    def timed(fn, warm, iters):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(iters):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return sorted(ts)[len(ts) // 2]
-
+    x = torch.randn(1, n, c, device=dev).to(torch.bfloat16)
     with torch.no_grad():
-        ms = timed(lambda: model(x, ei), 2, 5)
-    e1 = gw.grid_edge_count(h, wd)
-    out["full_forward_cfg3"] = {
-        "workload": "cfg3: COSMO-1E grid 1158x774 (896292 nodes, E'=%d), six GCN layers 64-1024-512-256-512-1024-64, bf16, "
-                    "8 ensemble members per step, synthetic data, random-init weights" % e1,
-        "ms_per_step": ms, "grid_steps_per_s": 1e3 / ms, "member_steps_per_s": b * 1e3 / ms,
-        "edges_per_s": b * e1 * 6 / (ms * 1e-3),
-        "flops_per_step": 2.0 * b * n * 1441792, "tflops": 2.0 * b * n * 1441792 / (ms * 1e-3) / 1e12}
-    del x
-    model = model.float()          # config 5: bf16 activations, fp32 master weights (cast to bf16 per call)
-    x1 = torch.randn(1, n, c, device=dev).to(torch.bfloat16)
-    mask = (torch.arange(n, device=dev) % 125) == 124
+        ms_f = _timed(lambda: model(x, ei), 2, 5)
 
-    def train_step():
-        gw.train_step(model, x1, ei, mask)     # zero_grad, forward, fused masked L1 vs the input, backward
-
-    ms_t = timed(train_step, 2, 3)
-    out["train_step_cfg5_member"] = {
-        "workload": "cfg5 shape, one member: gwen_b200.train_step = forward + fused masked-L1 loss (target = input, "
-                    "mask id%125==124) + backward through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16 activations, "
-                    "fp32 master weights and fp32 weight gradients, optimizer step excluded",
-        "ms_per_member_step": ms_t, "member_steps_per_s": 1e3 / ms_t}
+    def train():
+        for p in model.parameters():
+            p.grad = None
+        model(x, ei).float().abs().mean().backward()
+    ms_t = _timed(train, 1, 3)
+    del model, x
     gw.clear_graph_cache()
-    return out
+    torch.cuda.empty_cache()
+    return {"workload": "cfg4: 2048x2048 mesh (4194304 nodes), six layers, bf16, B=1, FIXED global size (strong scaling); "
+                        "N=1: un-partitioned model", "n_gpus": 1, "fwd_ms": ms_f, "fwd_bwd_allreduce_ms": ms_t,
+            "note": "N=1 has no all-reduce; the N>1 bench lines carry the same keys for the same global mesh"}
+
+
+# ---------------------------------------------------------------------------------------------
+# other_configs, N > 1 (collective: every rank calls these)
+# ---------------------------------------------------------------------------------------------
+def _timed_dist(fn, warm, iters, dev):
+    import torch
+    import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item()
+
+
+def _graphed(fn, dev):
+    """fn captured in a CUDA graph (all ranks' launches queued ahead of the GPUs: the partitioned step is
+    ~100 short kernels per rank and becomes launch-bound at N = 8).  Returns (callable, mode string)."""
+    import torch
+    try:
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream())
+        gobj = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(gobj, stream=cap):
+                fn()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        return gobj.replay, "CUDA graph replay"
+    except Exception as e:  # noqa: BLE001
+        print("bench: graph capture failed (%s); eager launches" % str(e)[:200], file=sys.stderr)
+        torch.cuda.synchronize()
+        return fn, "eager launches (graph capture failed)"
+
+
+def probe_strong_cfg4(dev, world, rank):
+    import torch
+    import torch.distributed as dist
+    import gwen_b200 as gw
+    from gwen_b200 import partition
+    h = wd = 2048
+    n, c = h * wd, 64
+    gw.clear_graph_cache()
+    ei = gw.grid(h, wd, dev)
+    g = gw.get_graph(ei, n)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
+    torch.manual_seed(23)
+    model = gw.GNNModel(cfg).to(dev).to(torch.bfloat16)
+    band = partition.PeerMeshBand(h, wd, g.dis)
+    net = partition.BandGNNModel(model, band)
+    del ei, g
+    gw.clear_graph_cache()
+    xo = torch.randn(1, band.n_own, c, device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ms_f = _timed_dist(lambda: net(xo), 3, 5, dev)
+
+    def train():
+        for p in model.parameters():
+            p.grad = None
+        net(xo).float().abs().mean().backward()
+        net.allreduce_grads()
+    ms_t = _timed_dist(train, 2, 3, dev)
+    res = {"workload": "cfg4: 2048x2048 mesh (4194304 nodes), six layers, bf16, B=1, FIXED global size (strong scaling), "
+                       "row bands over %d GPUs, halo rows pulled over NVLink inside the aggregation kernels, weight "
+                       "gradients all-reduced per layer under the remaining backward" % world,
+           "n_gpus": world, "fwd_ms": ms_f, "fwd_bwd_allreduce_ms": ms_t, "step_launch": "eager launches",
+           "peer_error_word": band.error_word()}
+    # the same step replayed from a CUDA graph (no host launch latency between the ~100 short kernels)
+    try:
+        with torch.no_grad():
+            fwd_g, mode_f = _graphed(lambda: net(xo), dev)
+            if mode_f.startswith("CUDA graph"):
+                res["fwd_ms_graph"] = _timed_dist(fwd_g, 2, 5, dev)
+    except Exception as e:  # noqa: BLE001
+        res["graph_error"] = str(e)[:200]
+    del model, net, band, xo
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
+def probe_train_cfg5(dev, world, rank, batch=21):
+    import torch
+    import torch.distributed as dist
+    import gwen_b200 as gw
+    from gwen_b200 import partition
+    h, wd, c = 1158, 774, 64
+    n = h * wd
+    gw.clear_graph_cache()
+    ei = gw.grid(h, wd, dev)
+    g = gw.get_graph(ei, n)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=1024)
+    torch.manual_seed(23)
+    model = gw.GNNModel(cfg).to(dev)                  # fp32 master weights, bf16 activations
+    band = partition.PeerMeshBand(h, wd, g.dis)
+    net = partition.BandGNNModel(model, band)
+    del ei, g
+    gw.clear_graph_cache()
+    xo = torch.randn(batch, band.n_own, c, device=dev).to(torch.bfloat16)
+    ids = torch.arange(band.r0 * wd, (band.r0 + band.rows) * wd, device=dev)
+    mo = (ids % 125) == 124
+
+    def train():
+        for p in model.parameters():
+            p.grad = None
+        net.loss(net(xo), xo, mo).backward()
+        net.allreduce_grads()
+    ms_t = _timed_dist(train, 2, 3, dev)
+    res = {"workload": "cfg5: COSMO-1E grid 1158x774, training step (forward + masked L1 vs the input + backward + "
+                       "gradient all-reduce), %d-member ensemble batch, bf16 activations / fp32 master weights, mesh "
+                       "partitioned into row bands over %d GPUs; optimizer step excluded" % (batch, world),
+           "n_gpus": world, "train_step_ms": ms_t, "member_steps_per_s": batch * 1e3 / ms_t,
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9, "peer_error_word": band.error_word()}
+    del model, net, band, xo
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -229,6 +492,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import gwen_b200 as gw
+    from gwen_b200 import graph as gwgraph
     from gwen_b200 import ops, partition
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,44 +523,74 @@ def run_ours(args):
     g_global = gw.build_graph(ei, gh * W)
     launches_per_step = 1
     band = None
+    halo_mode = None
+    partition_parity = None
     if world == 1:
-        graph, n_local, n_own = g_global, H * W, H * W
+        graph, n_own = g_global, H * W
         msgs_local = graph.num_messages
         assert graph.is_plain_mesh
-        x = torch.randn(n_own, FEAT, generator=gen).to(dev)
-        x_own = x
+        x0 = torch.randn(n_own, FEAT, generator=gen).to(dev)
+        xs = [x0] + [x0.clone() for _ in range(NBUF - 1)]
+        x_own = x0
     else:
         halo_mode = args.halo
-        band = None
         if halo_mode == "peer":
             try:      # CUDA symmetric memory (peer mappings of the neighbours' buffers)
                 band = partition.PeerMeshBand(gh, W, g_global.dis)
-                xs = [band.alloc(1, FEAT, torch.float32, dev) for _ in range(2)]
+                xs = [band.alloc(1, FEAT, torch.float32, dev) for _ in range(NBUF)]
             except Exception as e:  # noqa: BLE001  (uniform across ranks: same driver / same box)
                 print("bench: symmetric memory unavailable (%s); using the NCCL halo exchange" % str(e)[:200],
                       file=sys.stderr)
                 halo_mode, band = "nccl", None
         if band is None:
             band = partition.MeshBand(gh, W, g_global.dis)
-            xs = [band.alloc(1, FEAT, torch.float32, dev) for _ in range(2)]
-        n_own, n_local = band.n_own, band.n_local
+            xs = [band.alloc(1, FEAT, torch.float32, dev) for _ in range(NBUF)]
+        n_own = band.n_own
         ranges = partition.band_ranges(gh, W, world)
         rp = g_global.rowptr
         msgs_local = int((rp[ranges[rank].stop] - rp[ranges[rank].start]).item())
         # peer: ONE launch (halo fetch inside); nccl: interior + first-row + last-row launches
         launches_per_step = 1 if halo_mode == "peer" else 3
-        del g_global, ei
-        x = xs[0]                                                           # xs: ping-pong for the e2e leg
-        x_own = band.owned(x[0])
+        x_own = band.owned(xs[0][0])
         x_own.copy_(torch.randn(n_own, FEAT, generator=gen).to(dev))
-        band.owned(xs[1][0]).copy_(x_own)
-    out = torch.empty(n_own, FEAT, device=dev)
+        for t in xs[1:]:
+            band.owned(t[0]).copy_(x_own)
+        # ---- partition parity: this rank's band of the partitioned aggregation, BITWISE against the
+        # single-GPU stencil on the same global input.  The neighbours' boundary rows travel by NCCL
+        # send/recv here (not through the kernel under test); the single-GPU launch sees the rows
+        # [r0 - 1, r0 + rows + 1) of the global mesh with the GLOBAL dis.
+        torch.cuda.synchronize()
+        dist.barrier()
+        y_band = band.aggregate(xs[0], bias).clone()
+        rows = band.rows
+        chk = torch.zeros((rows + 2) * W, FEAT, device=dev)
+        chk[W:(rows + 1) * W].copy_(x_own)
+        p2p = []
+        if band.up is not None:
+            p2p += [dist.P2POp(dist.isend, x_own[:W].contiguous(), band.up), dist.P2POp(dist.irecv, chk[:W], band.up)]
+        if band.down is not None:
+            p2p += [dist.P2POp(dist.isend, x_own[(rows - 1) * W:].contiguous(), band.down),
+                    dist.P2POp(dist.irecv, chk[(rows + 1) * W:], band.down)]
+        for req in dist.batch_isend_irecv(p2p):
+            req.wait()
+        d2 = g_global.dis.view(gh, W)
+        loc = torch.zeros((rows + 2, W), device=dev)
+        lo, hi = max(band.r0 - 1, 0), min(band.r0 + rows + 1, gh)
+        loc[lo - (band.r0 - 1):hi - (band.r0 - 1)] = d2[lo:hi]
+        y_single = ops.mesh_stencil(chk.unsqueeze(0), gwgraph.bordered_dis(loc), rows + 2, rows, W, 1, bias=bias)
+        okt = torch.tensor([1.0 if torch.equal(y_single.view(-1), y_band.view(-1)) else 0.0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        partition_parity = bool(okt.item() == 1.0)
+        del chk, y_single, y_band, loc
+        del g_global, ei
+    outs = [torch.empty(n_own, FEAT, device=dev) for _ in range(NBUF)]
 
-    def step():
+    def make_step(i):
         if band is not None:
-            band.aggregate(x, bias, out=out)  # halo exchange on a side stream under the interior rows
-        else:
-            ops.aggregate(graph, x, bias, kernel="stencil", out=out)
+            return lambda: band.aggregate(xs[i], bias, out=outs[i])
+        return lambda: ops.aggregate(graph, xs[i], bias, kernel="stencil", out=outs[i])
+
+    steps_fn = [make_step(i) for i in range(NBUF)]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -304,97 +598,128 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    for i in range(max(args.warmup, 3)):
+        steps_fn[i % NBUF]()
     sync_all()
     step_mode = "eager launches"
     if band is not None:
-        # Capture the partitioned step once in a CUDA graph and replay it, so that all ranks' launches
-        # are queued ahead of the GPU (peer: the ranks' kernels wait on one another's flags; nccl:
-        # the step is ~8 host-side operations for ~100 us of GPU work).
-        eager_step = step
-        try:
-            cap = torch.cuda.Stream()
-            cap.wait_stream(torch.cuda.current_stream())
-            graph_obj = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(cap):
-                with torch.cuda.graph(graph_obj, stream=cap):
-                    eager_step()
-            torch.cuda.current_stream().wait_stream(cap)
-            step = graph_obj.replay
-            for _ in range(3):
-                step()
-            step_mode = "CUDA graph replay of the partitioned step"
-        except Exception as e:  # noqa: BLE001
-            print("bench: CUDA graph capture failed (%s); timing eager launches" % str(e)[:200], file=sys.stderr)
-            step = eager_step
+        # Capture each buffer's partitioned step once in a CUDA graph and replay it, so that all ranks'
+        # launches are queued ahead of the GPU (peer: the ranks' kernels wait on one another's flags;
+        # nccl: the step is ~8 host-side operations for ~100 us of GPU work).
+        graphed, modes = [], []
+        for fn in steps_fn:
+            g_fn, mode = _graphed(fn, dev)
+            graphed.append(g_fn)
+            modes.append(mode)
+        if all(m.startswith("CUDA graph") for m in modes):
+            steps_fn = graphed
+            step_mode = "CUDA graph replay of the partitioned step (one graph per buffer pair)"
+            for i in range(NBUF):
+                steps_fn[i]()
+        else:
             step_mode = "eager launches (graph capture failed)"
         sync_all()
+
+    def timed_region(k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            steps_fn[i % NBUF]()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
     t_wall0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms_total = timed_region(args.steps)
     tot = torch.tensor([float(msgs_local)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.barrier()
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_total = ms.item()
     total_msgs = tot.item()
     value = total_msgs * args.steps / (ms_total * 1e-3)
+    long_run = None
+    if args.steps < LONG_STEPS:
+        ms_long = timed_region(LONG_STEPS)
+        long_run = {"steps": LONG_STEPS, "ms_per_step": ms_long / LONG_STEPS,
+                    "value": total_msgs * LONG_STEPS / (ms_long * 1e-3),
+                    "note": "a second, longer timed region of the same step (the K-step region above is %.1f ms)" % ms_total}
 
-    # ---- launch duration of the dominant kernel: the timed region above is K back-to-back launches
-    # of it on the launching stream (one stencil launch per step at N = 1 and in peer mode), so its
-    # average duration is the CUDA-event time of the region / K.  (Events around single launches
+    # ---- launch duration of the dominant kernel: a timed region is back-to-back launches of it on the
+    # launching stream (one stencil launch per step at N = 1 and in peer mode), so its average duration is
+    # the CUDA-event time of the region / steps; the longer region is used.  (Events around single launches
     # would add the host launch latency to every sample.)  nccl mode: 3 launches per step, timed
     # separately below on the whole band.
     if launches_per_step == 1:
-        k_us = ms_total / args.steps * 1e3
+        k_us = (long_run["ms_per_step"] if long_run else ms_total / args.steps) * 1e3
     else:
         per = []
         for _ in range(min(50, max(10, args.steps))):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ops.mesh_stencil(x[0, :band.n_local], band.dis, band.rows + 2, band.rows, W, 1, bias=bias, out=out)
+            ops.mesh_stencil(xs[0][0, :band.n_local], band.dis, band.rows + 2, band.rows, W, 1, bias=bias, out=outs[0])
             b.record()
             per.append((a, b))
         torch.cuda.synchronize()
         k_us = statistics.mean(a.elapsed_time(b) for a, b in per) * 1e3
-    alg_bytes = 2 * n_own * FEAT * 4 + 4 * (n_own + 1) + 8 * msgs_local + 4 * FEAT
-    peak, peak_src = measured_peak()
+    # 2 N F s (rows once in, once out) + 4 (N + 1) rowptr + 4 E' src + 4 N dis
+    alg_bytes = 2 * n_own * FEAT * 4 + 4 * (n_own + 1) + 4 * msgs_local + 4 * n_own
+    # what the mesh-stencil kernel itself has to move (it never reads rowptr / src): rows + dis + bias
+    moved_bytes = 2 * n_own * FEAT * 4 + 4 * n_own + 4 * FEAT
+    peak, _, peak_src = measured_peaks()
     achieved = alg_bytes / (k_us * 1e-6) / 1e9
 
     # ---- e2e: public API with pinned host buffers, H2D + D2H inside the timed region ----------
-    x_host = torch.empty(n_own, FEAT).pin_memory()
+    if world > 1:
+        x_host = gw.pinned_near_gpu((n_own, FEAT), torch.float32, local_rank)   # pages on the GPU's NUMA node
+        out_host = gw.pinned_near_gpu((n_own, FEAT), torch.float32, local_rank)
+    else:
+        x_host = torch.empty(n_own, FEAT).pin_memory()
+        out_host = torch.empty(n_own, FEAT).pin_memory()
     x_host.copy_(x_own)
-    out_host = torch.empty(n_own, FEAT).pin_memory()
     conv = gw.GCNConv(FEAT, FEAT).to(dev)
     with torch.no_grad():
         conv.bias.copy_(bias)
-
+    e2e_api = None
+    if band is None:
+        # chunked H2D -> stencil -> D2H pipeline (gwen_b200/host_stream.py): the two PCIe
+        # directions and the kernel overlap, within a call and across calls
+        host_prop = gw.HostPropagator(graph, FEAT, torch.float32, chunks=8)
+        e2e_api = "gwen_b200.HostPropagator(graph, F)(x_host, out_host, bias): pinned host x / out, 8 row chunks, H2D / aggregate / D2H overlapped"
+    elif halo_mode == "peer":
+        host_prop = gw.HostBandPropagator(band, FEAT, torch.float32, chunks=8)
+        e2e_api = ("gwen_b200.HostBandPropagator(band, F)(x_host, out_host, bias): pinned host buffers on the GPU's NUMA node, "
+                   "8 row chunks, H2D / sub-range stencil / D2H overlapped, first+last band row from one peer launch")
+    else:
+        host_prop = None
+        e2e_api = "MeshBand.aggregate between a plain H2D and D2H"
     e2e_i = [0]
-    host_prop = gw.HostPropagator(graph, FEAT, torch.float32, chunks=8) if band is None else None
 
     def e2e_step():
-        if band is not None:
-            # a neighbour reads this rank's boundary rows during ITS launch: alternate two buffers so
-            # that the next step's H2D copy never overwrites rows a neighbour may still be reading
-            xb = xs[e2e_i[0] & 1]
+        if host_prop is not None:
+            host_prop(x_host, out_host, conv.bias)
+        else:
+            xb = xs[e2e_i[0] % NBUF]
             e2e_i[0] += 1
             band.owned(xb[0]).copy_(x_host, non_blocking=True)
             y = band.aggregate(xb, conv.bias)
             out_host.copy_(y.view(n_own, FEAT), non_blocking=True)
-        else:
-            # chunked H2D -> stencil -> D2H pipeline (gwen_b200/host_stream.py): the two PCIe
-            # directions and the kernel overlap, within a call and across calls
-            host_prop(x_host, out_host, conv.bias)
 
     for _ in range(3):
         e2e_step()
+    sync_all()
+    e2e_ok = None
+    if world > 1 or True:
+        # the e2e result must be the device-path result (bitwise): checked once, outside the timed region
+        ref_out = (band.aggregate(xs[0], conv.bias) if band is not None
+                   else ops.aggregate(graph, xs[0], conv.bias, kernel="stencil")).view(n_own, FEAT)
+        torch.cuda.synchronize()
+        e2e_ok = bool(torch.equal(out_host, ref_out.cpu()))
+        del ref_out
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
     for _ in range(args.e2e_steps):
@@ -407,9 +732,34 @@ def run_ours(args):
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = total_msgs * args.e2e_steps / (ms_e.item() * 1e-3)
     t_wall1 = time.time()
+    del host_prop
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- other_configs (collective at N > 1) ---------------------------------------------------
+    other = {}
+    if not args.no_model_probes:
+        del xs, outs, steps_fn
+        if world == 1:
+            del x0
+        torch.cuda.empty_cache()
+        probes = []
+        if world == 1:
+            probes = [("full_forward_cfg3", lambda: probe_full_forward_cfg3(dev)),
+                      ("train_step_cfg5_member", lambda: probe_train_member_cfg5(dev)),
+                      ("strong_cfg4", lambda: probe_cfg4_single(dev))]
+        elif halo_mode == "peer":
+            probes = [("strong_cfg4", lambda: probe_strong_cfg4(dev, world, rank))]
+            if world >= 4:
+                probes.append(("train_step_cfg5", lambda: probe_train_cfg5(dev, world, rank)))
+        for name, fn in probes:
+            try:
+                other[name] = fn()
+            except Exception as e:  # noqa: BLE001  (context only: never fail the headline line)
+                other[name] = {"error": str(e)[:300]}
+                if world > 1:
+                    break           # a collective probe failed on this rank: do not start the next one
 
     if rank == 0:
-        clocks = sampler.stop(t_wall0, t_wall1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -417,7 +767,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD if world == 1 else WORKLOAD + "; weak scaling: one 582x390 "
                        "row band per rank of a %dx390 mesh, one-row halo exchange per step (%s)" % (gh, "inside the aggregation kernel: one warp per CTA pulls the neighbours' boundary rows over NVLink peer memory under the interior tiles, device-side flags" if halo_mode == "peer" else "NCCL send/recv on a side stream under the interior rows"),
-                       "l2": "inputs+outputs 465 MB per rank > 126 MB L2, no explicit flush",
+                       "l2": "the step rotates over %d input/output buffer pairs (%.0f MB per rank > 126 MB L2): no line survives "
+                             "in L2 between two uses of a buffer, no explicit flush" % (NBUF, NBUF * 2 * n_own * FEAT * 4 / 1e6),
                        "step_launch": step_mode,
                        "kernel": "k_grid_stencil (mesh fast path: 8x16 tiles, one 4-D TMA box per tile/slab, "
                                  "separable column sums in packed fp32x2 registers); exact CSR kernels "
@@ -425,21 +776,29 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": out_host.numel() * 4 * world, "steps": args.e2e_steps,
-                    "api": "gwen_b200.HostPropagator(graph, F)(x_host, out_host, bias): pinned host x / out, 8 row chunks, H2D / aggregate / D2H overlapped (N>1: PeerMeshBand.aggregate between a plain H2D and D2H)"},
+                    "gbs_per_direction_per_gpu": x_host.numel() * 4 * args.e2e_steps / (ms_e.item() * 1e-3) / 1e9,
+                    "result_equals_device_path": e2e_ok, "api": e2e_api},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"kernel": "k_grid_stencil<float,16>", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "peak_source": peak_src,
                          "us_per_launch": k_us, "algorithmic_bytes_per_launch": alg_bytes,
-                         "traffic": ncu_traffic()},
+                         "algorithmic_bytes_formula": "SURVEY 8(d): 2*N*F*4 + 4*(N+1) + 4*E' + 4*N",
+                         "bytes_moved_by_kernel": moved_bytes,
+                         "frac_bytes_moved_by_kernel": moved_bytes / (k_us * 1e-6) / 1e9 / peak,
+                         "bytes_moved_formula": "2*N*F*4 + 4*N (dis) + 4*F (bias): the mesh kernel never reads rowptr/src",
+                         "traffic": None,
+                         "traffic_source": "not measured in this run; the committed ncu capture is profiles/r02_k_grid_stencil_cfg2.md "
+                                           "(dram__bytes_read.sum + dram__bytes_write.sum per launch)"},
         }
-        if world == 1 and not args.no_model_probes:
-            try:
-                del x, out
-                torch.cuda.empty_cache()
-                line["other_configs"] = model_probes(dev)
-            except Exception as e:  # noqa: BLE001  (context only: never fail the headline line)
-                line["other_configs"] = {"error": str(e)[:300]}
+        if long_run is not None:
+            line["long_run"] = long_run
+        if partition_parity is not None:
+            line["partition_parity"] = partition_parity
+            line["partition_parity_what"] = ("every rank's band of the partitioned aggregation is bitwise equal to the "
+                                             "single-GPU stencil on the same global input (neighbour rows sent by NCCL for the check)")
+        if other:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             rate, per_step, edges, cores = cpu_propagate_rate(H, 3, warmup=1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

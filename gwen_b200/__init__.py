@@ -12,11 +12,11 @@ from .models_gnn import (DownConvLayers, GCNConvLayers, GNNConfig, GNNModel, UpC
                          loss_func)
 from . import ops  # noqa: F401
 from . import partition  # noqa: F401
-from .host_stream import HostPropagator
+from .host_stream import HostBandPropagator, HostPropagator, pinned_near_gpu
 from .train import eval_step, gather_eval_results, masked_l1_loss, train_step
 from .data import GraphDataset
 
 __version__ = "0.1.0"
 __all__ = ["GCNConv", "gcn_conv", "GraphCSR", "build_graph", "get_graph", "clear_graph_cache",
-           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "masked_l1_loss", "train_step", "eval_step", "gather_eval_results", "GraphDataset", "GNNConfig",
+           "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "HostBandPropagator", "pinned_near_gpu", "masked_l1_loss", "train_step", "eval_step", "gather_eval_results", "GraphDataset", "GNNConfig",
            "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops", "partition"]

@@ -27,6 +27,9 @@ def nvcc_command(out_path: str = LIB_PATH) -> list:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
             "--expt-relaxed-constexpr", "--threads", "0", "-Xcompiler", "-fPIC", "-shared",
+            # the CUDA runtime is the process's shared one (torch has loaded libcudart.so.12 by the time this
+            # library is opened): no second static copy of the runtime inside the product binary
+            "--cudart", os.environ.get("GWEN_CUDART", "shared"),
             "-I" + os.path.join(_ROOT, "include"), "-o", out_path] + \
         [os.path.join(CSRC, s) for s in SOURCES]
 
@@ -92,11 +95,11 @@ PROTOTYPES = {
     "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _i64, _i64, _i64,
                                         _i64, _i64, _i64, _i64, _int, _p, _int, _i32, _i32, _i32,
                                         _p]),
-    "gwen_grid_stencil_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+    "gwen_grid_stencil_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                      _i64, _i64, _int, _p, _int, _i32, _i32, _p]),
-    "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+    "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                           _int, _p, _int, _i32, _i32, C.POINTER(HaloPeersStruct), _p]),
-    "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
+    "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_fwd_workspace_bytes": (_int, [_i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "gwen_linear_fwd_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _sz, _p]),
@@ -115,7 +118,7 @@ PROTOTYPES = {
     "gwen_bias_grad_workspace_bytes": (_int, [_i64, _i64, C.POINTER(_sz)]),
     "gwen_relu_bias_bwd": (_int, [_p, _p, _p, _p, _i64, _i64, _int, _p, _sz, _p]),
     "gwen_masked_l1_workspace_bytes": (_int, [_i64, C.POINTER(_sz)]),
-    "gwen_masked_l1_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
+    "gwen_masked_l1_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _sz, _p]),
     "gwen_masked_l1_bwd": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p]),
     "gwen_rows_gather": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_rows_scatter": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),

@@ -333,7 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
 using namespace gwen;
 
 extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* dis_padded,
-                                  int64_t dis_pitch, int64_t batch, int64_t h, int64_t w, int64_t k_in,
+                                  int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t h, int64_t w, int64_t k_in,
                                   int64_t n_out, int dtype, const float* bias, int epilogue,
                                   void* stream) {
   GWEN_CHECK_ARG(batch >= 0 && h >= 0 && w >= 0 && k_in >= 0 && n_out >= 0, "negative size");
@@ -349,6 +349,7 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   const int k_blocks = static_cast<int>(k_in / 64);
   const int tiles_y = static_cast<int>(ceil_div(h, TH)), pairs_x = static_cast<int>(ceil_div(w, 2 * FT_W));
   GWEN_CHECK_ARG(dis_pitch >= int64_t(pairs_x) * 2 * FT_W + 4, "bordered dis pitch too small");
+  GWEN_CHECK_ARG(dis_rows >= int64_t(tiles_y) * TH + 2, "bordered dis has too few rows");
   // N tile: 256 columns unless the resident A block (k_in = 512) leaves no room for 16 KB W stages
   const size_t fixed = 2 * size_t(k_blocks) * kABlock + 2 * kSrcStage + 8 * 2048 + align_up(size_t(n_out) * 4, 1024) + 1024;
   const size_t cap = 226 * 1024;

@@ -21,7 +21,7 @@ constexpr int kThreads = 256;
 
 struct GraphWs {
   int64_t total;  // E + (self ? N : 0)
-  size_t off_keys_in, off_keys_out, off_vals_in, off_vals_out, off_pos, off_cub, cub_bytes, bytes;
+  size_t off_keys_in, off_keys_out, off_vals_in, off_vals_out, off_pos, off_loop, off_cub, cub_bytes, bytes;
 };
 
 int key_bits(int64_t n) {
@@ -45,6 +45,7 @@ cudaError_t plan_ws(int64_t n, int64_t e, uint32_t flags, GraphWs* p) {
   p->off_vals_in = take(t * 4);
   p->off_vals_out = take(t * 4);
   p->off_pos = take((static_cast<size_t>(e) + 1) * 4);
+  p->off_loop = take(static_cast<size_t>(n > 0 ? n : 1));  // had_loop[n]: node had a self loop in the input
   size_t sort_bytes = 0, scan_bytes = 0;
   cudaError_t err = cub::DeviceRadixSort::SortPairs(
       nullptr, sort_bytes, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
@@ -63,7 +64,7 @@ cudaError_t plan_ws(int64_t n, int64_t e, uint32_t flags, GraphWs* p) {
 __global__ void k_prepare(const int64_t* __restrict__ ei, int64_t e, int64_t n, int64_t total,
                           bool self, bool transpose, int32_t* __restrict__ keys,
                           int32_t* __restrict__ vals, int32_t* __restrict__ pos,
-                          int32_t* __restrict__ status) {
+                          unsigned char* __restrict__ had_loop, int32_t* __restrict__ status) {
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i == 0) pos[e] = 0;
   if (i >= total) return;
@@ -72,6 +73,7 @@ __global__ void k_prepare(const int64_t* __restrict__ ei, int64_t e, int64_t n, 
     bool ok = r >= 0 && r < n && c >= 0 && c < n;
     if (!ok) atomicAdd(&status[0], 1);
     bool keep = ok && (!self || r != c);
+    if (ok && self && r == c) had_loop[r] = 1;  // add_remaining_self_loops keeps an existing loop's weight (1)
     int64_t dst = transpose ? r : c;
     keys[i] = keep ? static_cast<int32_t>(dst) : static_cast<int32_t>(n);
     pos[i] = keep ? 1 : 0;
@@ -111,13 +113,17 @@ __global__ void k_fill(const int64_t* __restrict__ ei, int64_t e, int64_t n, int
   }
 }
 
+// deg = sum of edge weights into i: 1 per surviving edge; the appended self loop weighs `loop_fill`
+// (2 for improved=True) unless the input already held a self loop of i, whose weight 1 is kept
+// (PyG add_remaining_self_loops: loop_attr[existing] = edge_attr[existing]).
 __global__ void k_dis(const int32_t* __restrict__ rowptr, int64_t n, int extra_deg,
-                      float* __restrict__ dis, int32_t* __restrict__ status) {
+                      const unsigned char* __restrict__ had_loop, float* __restrict__ dis,
+                      int32_t* __restrict__ status) {
   int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (i == 0) status[1] = rowptr[n];
   if (i >= n) return;
   int32_t cnt = rowptr[i + 1] - rowptr[i];
-  double deg = double(cnt > 0 ? cnt + extra_deg : 0);
+  double deg = double(cnt > 0 ? cnt + (had_loop[i] ? 0 : extra_deg) : 0);
   dis[i] = deg > 0.0 ? static_cast<float>(1.0 / sqrt(deg)) : 0.0f;
 }
 
@@ -125,12 +131,12 @@ __global__ void k_dis(const int32_t* __restrict__ rowptr, int64_t n, int extra_d
 __global__ void k_weights(const int32_t* __restrict__ keys, const int32_t* __restrict__ vals,
                           const int32_t* __restrict__ src, const float* __restrict__ dis,
                           int64_t e, int64_t n, int64_t total, float loop_fill,
-                          float* __restrict__ w) {
+                          const unsigned char* __restrict__ had_loop, float* __restrict__ w) {
   int64_t s = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (s >= total) return;
   int32_t k = keys[s];
   if (k >= n) return;
-  float fill = vals[s] >= e ? loop_fill : 1.0f;
+  float fill = (vals[s] >= e && !had_loop[k]) ? loop_fill : 1.0f;
   w[s] = __fmul_rn(__fmul_rn(dis[src[s]], fill), dis[k]);
 }
 
@@ -210,14 +216,16 @@ extern "C" int gwen_graph_build(const int64_t* edge_index, int64_t e, int64_t n,
   int32_t* vals_in = reinterpret_cast<int32_t*>(base + p.off_vals_in);
   int32_t* vals_out = reinterpret_cast<int32_t*>(base + p.off_vals_out);
   int32_t* pos = reinterpret_cast<int32_t*>(base + p.off_pos);
+  unsigned char* had_loop = reinterpret_cast<unsigned char*>(base + p.off_loop);
   void* cub_ws = base + p.off_cub;
+  GWEN_CUDA(cudaMemsetAsync(had_loop, 0, static_cast<size_t>(n > 0 ? n : 1), stream));
 
   GWEN_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(int32_t), stream));
   GWEN_CUDA(cudaMemsetAsync(rowptr, 0, (n + 1) * sizeof(int32_t), stream));
   const int64_t total = p.total;
   const unsigned grid_t = static_cast<unsigned>(ceil_div(total > 0 ? total : 1, kThreads));
   k_prepare<<<grid_t, kThreads, 0, stream>>>(edge_index, e, n, total, self, transpose, keys_in,
-                                             vals_in, pos, status);
+                                             vals_in, pos, had_loop, status);
   GWEN_LAUNCH_CHECK("k_prepare");
   size_t cub_bytes = p.cub_bytes;
   GWEN_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, pos, pos, static_cast<int>(e + 1),
@@ -235,7 +243,7 @@ extern "C" int gwen_graph_build(const int64_t* edge_index, int64_t e, int64_t n,
   }
   const unsigned grid_n = static_cast<unsigned>(ceil_div(n > 0 ? n : 1, kThreads));
   if (!transpose) {
-    k_dis<<<grid_n, kThreads, 0, stream>>>(rowptr, n, (self && improved) ? 1 : 0, dis, status);
+    k_dis<<<grid_n, kThreads, 0, stream>>>(rowptr, n, (self && improved) ? 1 : 0, had_loop, dis, status);
     GWEN_LAUNCH_CHECK("k_dis");
   } else {
     // dis is an INPUT here (the forward graph's in-degree normalisation); only record E'.
@@ -244,7 +252,7 @@ extern "C" int gwen_graph_build(const int64_t* edge_index, int64_t e, int64_t n,
   }
   if (w && total > 0) {
     k_weights<<<grid_t, kThreads, 0, stream>>>(keys_out, vals_out, src, dis, e, n, total,
-                                               improved ? 2.0f : 1.0f, w);
+                                               improved ? 2.0f : 1.0f, had_loop, w);
     GWEN_LAUNCH_CHECK("k_weights");
   }
   return GWEN_OK;

@@ -47,6 +47,7 @@ struct Tc3Args {
   int epi_groups;  // epilogue warp groups (of 4 warps) that work: 4, or 2 to trade staging for ring depth
   int batch;  // independent [m, k] x-slices / [m, n] y-slices (third TMA coordinate), same W
   int b_mn;  // B operand is MN-major: w is [reduction][n] row-major (dgrad: dx = dy W)
+  int epi_cols;  // output columns per epilogue chunk and TMA store: 32 (64-byte rows) or 64 (128-byte rows)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
@@ -61,13 +62,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
   const bool leader = rank == 0;
   const uint32_t a_bytes = BM * BK * 2, b_bytes = uint32_t(g.bn / 2) * BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t staging = base + uint32_t(g.stages) * stage_bytes;  // 16 warps x bufs x 2 KB
+  const uint32_t staging = base + uint32_t(g.stages) * stage_bytes;  // 16 warps x bufs x 2 KB (4 KB: 64-column chunks)
+  const uint32_t stg_bytes = g.epi_cols == 64 ? 4096u : 2048u;
   // the whole bias vector (n floats, zeros when absent) sits behind the staging buffers
   float* bias_s = reinterpret_cast<float*>(smem_raw + (staging - smem_u32(smem_raw)) +
-                                           size_t(4 * g.epi_groups) * 2048u * size_t(g.bufs));
+                                           size_t(4 * g.epi_groups) * stg_bytes * size_t(g.bufs));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = g.n / g.bn;
-  const int n_sub = g.bn / 32;  // 32-column epilogue sub-chunks per tile
+  const int n_sub = g.bn / g.epi_cols;  // epilogue sub-chunks per tile
   const int64_t mb_per_batch = (g.m + 2 * BM - 1) / (2 * BM);
   const int64_t m_blocks = mb_per_batch * g.batch;   // row blocks of all batch slices
   const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -174,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
   } else {
     // ===== epilogue warps 2..17: TMEM lanes 32*(warp%4) .. +31, 32-column sub-chunks g4, g4+4, .. =====
     const int q = warp & 3, g4 = (warp - 2) >> 2;
-    const uint32_t my_stage = staging + uint32_t(warp - 2) * 2048u * uint32_t(g.bufs);  // 2 KB buffers
+    const uint32_t my_stage = staging + uint32_t(warp - 2) * stg_bytes * uint32_t(g.bufs);
     const uint32_t row_off = uint32_t(lane) * 64u;
     const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk ^= (row / 2) % 4
     const bool relu = g.relu != 0;
@@ -192,6 +194,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
         mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
         tc_fence_after();
         const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
+        if (g.epi_cols == 64) {
+          // 64-column chunks: two TMEM loads fill one 32-row x 128-byte staging tile (SWIZZLE_128B), ONE TMA
+          // store of 128-byte rows per chunk -- half as many stores, each row a full 128-byte line (the
+          // write-bound shapes, K < 512, were limited by the store path at 64-byte rows)
+          const uint32_t sw7 = uint32_t(lane) & 7u;
+          for (int sc = g4; sc < n_sub; sc += g.epi_groups) {
+            const int c = sc * 64;
+            uint32_t r[32];
+            tmem_ld32_nowait(t_addr + uint32_t(c), r);
+            if (lane == 0) {
+              if (g.bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            __syncwarp();
+            const uint32_t sbuf = my_stage + buf * stg_bytes + uint32_t(lane) * 128u;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + c + 32 * half);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b0 = bp[2 * j], b1 = bp[2 * j + 1];
+                uint4 o;
+                o.x = bias_pack(r[8 * j + 0], r[8 * j + 1], b0.x, b0.y, relu);
+                o.y = bias_pack(r[8 * j + 2], r[8 * j + 3], b0.z, b0.w, relu);
+                o.z = bias_pack(r[8 * j + 4], r[8 * j + 5], b1.x, b1.y, relu);
+                o.w = bias_pack(r[8 * j + 6], r[8 * j + 7], b1.z, b1.w, relu);
+                sts_v4(sbuf + ((uint32_t(4 * half + j) ^ sw7) << 4), o);
+              }
+              if (half == 0) {
+                tmem_ld32_nowait(t_addr + uint32_t(c + 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (sc + g.epi_groups >= n_sub) {  // last TMEM read of this tile by this warp
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive_cluster(acc ? empty_remote1 : empty_remote0);
+                }
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&ymap, my_stage + buf * stg_bytes, n0 + c, m0 + q * 32, bi);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            buf = (buf + 1u) & uint32_t(g.bufs - 1);
+          }
+          continue;
+        }
         for (int sc = g4; sc < n_sub; sc += g.epi_groups) {
           const int c = sc * 32;
           uint32_t r[32];
@@ -265,8 +316,6 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   rc = b_mn ? make_tensor_map_3d(&bmap, w, GWEN_BF16, n_out, k, 1, ldw, 0, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B)
             : make_tensor_map_3d(&bmap, w, GWEN_BF16, k, n_out, 1, ldw, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
-  rc = make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-  if (rc != GWEN_OK) return rc;
   const int k_blocks = static_cast<int>(ceil_div(k, BK));
   const size_t stage_bytes = size_t(BM + bn / 2) * BK * 2;
   static const int bufs = [] {
@@ -280,7 +329,18 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
     return v ? atoi(v) : 0;
   }();
   const int epi_groups = (groups_env == 2 || groups_env == 4) ? groups_env : (k >= 512 ? 2 : 4);
-  const size_t staging_bytes = size_t(4 * epi_groups) * bufs * 2048 + align_up(size_t(n_out) * 4, 1024);
+  // write-bound shapes (shallow K: all 16 epilogue warps work) store 64-column chunks = 128-byte rows
+  static const int cols_env = [] {
+    const char* v = getenv("GWEN_TC3_EPI_COLS");
+    return v ? atoi(v) : 0;
+  }();
+  const int epi_cols = (cols_env == 32 || cols_env == 64) ? (bn % cols_env ? 32 : cols_env)
+                                                          : (epi_groups == 4 && bn % 64 == 0 ? 64 : 32);
+  rc = epi_cols == 64
+           ? make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)
+           : make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc != GWEN_OK) return rc;
+  const size_t staging_bytes = size_t(4 * epi_groups) * bufs * (epi_cols == 64 ? 4096 : 2048) + align_up(size_t(n_out) * 4, 1024);
   static const int stage_cap = [] {
     const char* v = getenv("GWEN_TC3_STAGES");
     return v ? std::max(2, std::min(kMaxStages, atoi(v))) : kMaxStages;
@@ -297,7 +357,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   }();
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
-  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn};
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn, epi_cols};
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kLossThreads) k_l1_partial(const T* __restrict
 // out[0] = loss, out[1] = 1 / (B * count * C) (the scale the backward pass uses)
 __global__ void __launch_bounds__(kLossThreads) k_l1_final(const float2* __restrict__ part, int blocks,
                                                            int64_t batch, int64_t feat,
+                                                           const float* __restrict__ count_override,
                                                            float* __restrict__ out) {
   __shared__ double s_sum[kLossThreads], s_cnt[kLossThreads];
   double a = 0.0, c = 0.0;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kLossThreads) k_l1_final(const float2* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const double denom = double(batch) * s_cnt[0] * double(feat);
+    const double denom = double(batch) * (count_override ? double(count_override[0]) : s_cnt[0]) * double(feat);
     out[0] = float(s_sum[0] / denom);   // 0 / 0 = NaN for an empty mask, like mean() of an empty tensor
     out[1] = float(1.0 / denom);
   }
@@ -108,8 +109,8 @@ extern "C" int gwen_masked_l1_workspace_bytes(int64_t n, size_t* out) {
 }
 
 extern "C" int gwen_masked_l1_fwd(const void* y, const void* target, const uint8_t* mask, int64_t batch,
-                                  int64_t n, int64_t feat, int dtype, float* loss_and_scale, void* ws,
-                                  size_t ws_bytes, void* stream) {
+                                  int64_t n, int64_t feat, int dtype, const float* count_override,
+                                  float* loss_and_scale, void* ws, size_t ws_bytes, void* stream) {
   GWEN_CHECK_ARG(batch >= 0 && n >= 0 && feat >= 0, "negative size");
   GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
   GWEN_CHECK_ARG(loss_and_scale && ws && (n == 0 || (y && target && mask)), "null pointer");
@@ -126,7 +127,7 @@ extern "C" int gwen_masked_l1_fwd(const void* y, const void* target, const uint8
         static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(target), mask, batch, n,
         feat, part);
   GWEN_LAUNCH_CHECK("k_l1_partial");
-  k_l1_final<<<1, kLossThreads, 0, st>>>(part, blocks, batch, feat, loss_and_scale);
+  k_l1_final<<<1, kLossThreads, 0, st>>>(part, blocks, batch, feat, count_override, loss_and_scale);
   GWEN_LAUNCH_CHECK("k_l1_final");
   return GWEN_OK;
 }

@@ -49,10 +49,18 @@ struct StencilArgs {
   uint32_t* flag_up_remote;   // where this rank announces "my x is ready" to the neighbours
   uint32_t* flag_down_remote;
   uint32_t* ctl;              // local control words, see gwen_halo_peers
+  uint64_t spin_timeout_ns;   // bound on every wait of the protocol (a sticky error word is set instead of hanging)
 };
 
 // control words of the peer-halo protocol (ctl[] in local device memory, zero-initialised)
-enum { CTL_FROM_UP = 0, CTL_FROM_DOWN = 1, CTL_EPOCH = 2, CTL_HALO_DONE = 3, CTL_CTAS_DONE = 4 };
+enum { CTL_FROM_UP = 0, CTL_FROM_DOWN = 1, CTL_EPOCH = 2, CTL_HALO_DONE = 3, CTL_CTAS_DONE = 4, CTL_ERROR = 5 };
+enum { PEER_ERR_NEIGHBOUR_FLAG = 1, PEER_ERR_HALO_DONE = 2 };
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
@@ -149,9 +157,18 @@ __global__ void __launch_bounds__(576, 1)
     for (int side = 0; side < 2; ++side) {
       const unsigned char* src = side ? a.down_src : a.up_src;
       if (!src) continue;
-      if (lane == 0)
-        while (int32_t(ld_acquire_sys(a.ctl + (side ? CTL_FROM_DOWN : CTL_FROM_UP)) - epoch1) < 0)
+      if (lane == 0) {
+        // bounded: a neighbour that launched a different sequence of peer calls (or died) must give a
+        // diagnosable failure, not a hung GPU -- on timeout the sticky error word is set and we go on
+        const uint64_t t0 = globaltimer_ns();
+        while (int32_t(ld_acquire_sys(a.ctl + (side ? CTL_FROM_DOWN : CTL_FROM_UP)) - epoch1) < 0) {
           __nanosleep(64);
+          if (globaltimer_ns() - t0 > a.spin_timeout_ns) {
+            atomicOr(a.ctl + CTL_ERROR, uint32_t(PEER_ERR_NEIGHBOUR_FLAG));
+            break;
+          }
+        }
+      }
       __syncwarp();
       const int64_t sb = side ? a.down_bstride_bytes : a.up_bstride_bytes;
       unsigned char* dst = a.x_base + (side ? a.bottom_off_bytes : 0);
@@ -184,7 +201,14 @@ __global__ void __launch_bounds__(576, 1)
         int b, t, slab;
         decode(gi, b, t, slab);
         if (!halo_ready && gi >= n_int_items) {  // first tile that reads a halo row
-          while (ld_acquire_gpu(a.ctl + CTL_HALO_DONE) < gridDim.x) __nanosleep(32);
+          const uint64_t t0 = globaltimer_ns();
+          while (ld_acquire_gpu(a.ctl + CTL_HALO_DONE) < gridDim.x) {
+            __nanosleep(32);
+            if (globaltimer_ns() - t0 > a.spin_timeout_ns) {   // a CTA of this grid never ran: see CTL_ERROR
+              atomicOr(a.ctl + CTL_ERROR, uint32_t(PEER_ERR_HALO_DONE));
+              break;
+            }
+          }
           asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores -> TMA reads
           halo_ready = true;
         }
@@ -314,8 +338,31 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
   const int64_t items = int64_t(a.num_tiles) * a.batch * a.slabs;
   const int grid = static_cast<int>(std::min<int64_t>(items, std::max(1, (sm_count() - sm_reserve()) * cps)));
   // consumer sub-warps = TH * tw / SEG units when possible: 16 consumer warps + 1 producer warp
-  kern<<<grid, a.peer ? 576 : 32 * (cw_env + 1), smem, st>>>(xmap, a);
-  GWEN_LAUNCH_CHECK("k_grid_stencil");
+  if (!a.peer) {
+    kern<<<grid, 32 * (cw_env + 1), smem, st>>>(xmap, a);
+    GWEN_LAUNCH_CHECK("k_grid_stencil");
+    return GWEN_OK;
+  }
+  // Peer mode: the CTAs wait for one another (every CTA publishes its halo share before the boundary
+  // tiles start), so the whole grid must be co-resident.  Clamp it to what the occupancy calculator
+  // says fits and launch COOPERATIVELY: the runtime then either schedules all CTAs together or
+  // fails the launch -- it never runs a part of the grid that would spin on the rest.
+  int per_sm = 0;
+  GWEN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 576, smem));
+  if (per_sm < 1) return set_err(GWEN_E_NOSUPPORT, "peer stencil does not fit on an SM");
+  const int grid_peer = std::min(grid, per_sm * sm_count());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid_peer);
+  cfg.blockDim = dim3(576);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GWEN_CUDA(cudaLaunchKernelEx(&cfg, kern, xmap, a));
+  GWEN_LAUNCH_CHECK("k_grid_stencil (peer)");
   return GWEN_OK;
 }
 
@@ -325,7 +372,7 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
 using namespace gwen;
 
 static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_t dis_pitch,
-                       int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
+                       int64_t dis_rows, int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
                        int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo, int64_t o_bstride,
                        int dtype, const float* bias, int epilogue, int32_t slab_elems,
                        int32_t tile_w, const gwen_halo_peers* peers, void* stream) {
@@ -334,6 +381,10 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
   GWEN_CHECK_ARG(x && out && dis_padded, "null pointer");
   GWEN_CHECK_ARG(dtype == GWEN_F32 || dtype == GWEN_BF16, "unknown dtype %d", dtype);
   GWEN_CHECK_ARG(row_off >= 0 && row_off + hd <= hs + 1, "row_off outside the source rows");
+  // every tile bulk-copies TH + 2 dis rows starting at bordered row r0 + row_off, r0 <= round_up(hd, TH) - TH
+  GWEN_CHECK_ARG(dis_rows >= (hd + TH - 1) / TH * TH + row_off + 2,
+                 "bordered dis has %lld rows, the launch reads %lld", (long long)dis_rows,
+                 (long long)((hd + TH - 1) / TH * TH + row_off + 2));
   GWEN_CHECK_ARG(dis_pitch % 4 == 0 && aligned16(dis_padded),
                  "bordered dis needs a pitch that is a multiple of 4 floats and a 16-byte base");
   GWEN_CHECK_ARG(hs * w < INT32_MAX && batch < 65536, "mesh too large");
@@ -402,6 +453,8 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
     a.flag_up_remote = peers->up_flag;
     a.flag_down_remote = peers->down_flag;
     a.ctl = peers->ctl;
+    static const int timeout_ms = env_int2("GWEN_PEER_TIMEOUT_MS", 10000, 1, 3600000);
+    a.spin_timeout_ns = uint64_t(timeout_ms) * 1000000ull;
   }
   if (dis_pitch < int64_t(tiles_x - 1) * tw + dis_box_w)
     return set_err(GWEN_E_BADARG, "bordered dis pitch %lld < %lld needed for tile width %d",
@@ -419,22 +472,22 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
 }
 
 extern "C" int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded,
-                                     int64_t dis_pitch, int64_t batch, int64_t hs, int64_t hd,
+                                     int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t hs, int64_t hd,
                                      int64_t w, int64_t row_off, int64_t feat, int64_t ldx,
                                      int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
                                      const float* bias, int epilogue, int32_t slab_elems,
                                      int32_t tile_w, void* stream) {
-  return stencil_fwd(x, out, dis_padded, dis_pitch, batch, hs, hd, w, row_off, feat, ldx, x_bstride,
+  return stencil_fwd(x, out, dis_padded, dis_pitch, dis_rows, batch, hs, hd, w, row_off, feat, ldx, x_bstride,
                      ldo, o_bstride, dtype, bias, epilogue, slab_elems, tile_w, nullptr, stream);
 }
 
 extern "C" int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded,
-                                          int64_t dis_pitch, int64_t batch, int64_t hd, int64_t w,
+                                          int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t hd, int64_t w,
                                           int64_t feat, int64_t x_bstride, int64_t ldo,
                                           int64_t o_bstride, int dtype, const float* bias,
                                           int epilogue, int32_t slab_elems, int32_t tile_w,
                                           const gwen_halo_peers* peers, void* stream) {
   GWEN_CHECK_ARG(peers != nullptr, "null halo peers");
-  return stencil_fwd(x, out, dis_padded, dis_pitch, batch, hd + 2, hd, w, 1, feat, feat, x_bstride,
+  return stencil_fwd(x, out, dis_padded, dis_pitch, dis_rows, batch, hd + 2, hd, w, 1, feat, feat, x_bstride,
                      ldo, o_bstride, dtype, bias, epilogue, slab_elems, tile_w, peers, stream);
 }

@@ -107,11 +107,14 @@ class TilePlan:
 
 
 def bordered_dis(dis2d: torch.Tensor) -> torch.Tensor:
-    """[H, W] -> zero-bordered fp32 [round_up(H, 8) + 4, pitch] as gwen_grid_stencil_fwd expects
-    (rows padded so the last 8-row tile can fetch its full box)."""
+    """[H, W] -> zero-bordered fp32 [H + 12, pitch] as gwen_grid_stencil_fwd expects.  The kernel
+    always bulk-copies the 10 dis rows of an 8-row tile, also for a sub-range launch whose last tile
+    starts at destination row ``round_up(hd, 8) - 8`` with ``row_off + hd <= H + 1``: the last row it
+    touches is ``round_up(hd, 8) + row_off + 1 <= H + 9``, so H + 12 rows cover every legal launch
+    (the C entry point checks ``dis_rows``)."""
     h, w = dis2d.shape
     pitch = (w + 128 + 8 + 3) // 4 * 4
-    d = torch.zeros(((h + 7) // 8 * 8 + 4, pitch), dtype=torch.float32, device=dis2d.device)
+    d = torch.zeros((h + 12, pitch), dtype=torch.float32, device=dis2d.device)
     d[1:h + 1, 1:w + 1] = dis2d
     return d
 

@@ -49,7 +49,31 @@ def _as_3d(x: torch.Tensor):
 def _bias32(bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if bias is None:
         return None
-    return bias.detach().to(torch.float32).contiguous()
+    return _cast_cached(bias, torch.float32)
+
+
+# Parameter casts (fp32 master weights -> bf16 operand, any bias -> fp32) are cached per parameter
+# VERSION: the cast kernel runs once after each optimizer update instead of once per layer call
+# (forward, dgrad and the recompute paths all ask for the same cast).  The cache holds weak references.
+_CAST_CACHE: dict = {}
+
+
+def _cast_cached(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype == dtype and t.is_contiguous():
+        return t
+    key = (id(t.untyped_storage()), t.storage_offset(), tuple(t.shape), tuple(t.stride()), dtype, t.device)
+    ent = _CAST_CACHE.get(key)
+    if ent is not None:
+        ref, ver, out = ent
+        if ref() is t.untyped_storage() and ver == t._version:
+            return out
+    import weakref
+    out = t.to(dtype).contiguous()
+    if len(_CAST_CACHE) > 256:
+        _CAST_CACHE.clear()
+    _CAST_CACHE[key] = (weakref.ref(t.untyped_storage()), t._version, out)
+    return out
 
 
 def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -88,7 +112,7 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
                 raise RuntimeError("the stencil kernel needs a plain H x W mesh graph")
             h, w = graph.grid_shape
             dpad = graph.dis_padded()
-            check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(out), _ptr(dpad), dpad.shape[1], b, h, h, w,
+            check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(out), _ptr(dpad), dpad.shape[1], dpad.shape[0], b, h, h, w,
                                               0, f, f, n_src * f, f, graph.n_dst * f, code,
                                               _ptr(bias32), epi, slab, tile[0] if tile else 0,
                                               _stream()), "gwen_grid_stencil_fwd")
@@ -120,7 +144,7 @@ def mesh_stencil(x: torch.Tensor, dis_bordered: torch.Tensor, hs: int, hd: int, 
         o3 = out if out.dim() == 3 else out.unsqueeze(0)
         assert o3.is_contiguous() or o3.stride(-1) == 1
         check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(o3), _ptr(dis_bordered), dis_bordered.shape[1],
-                                          b, hs, hd, w, row_off, f, f, n_src * f, f, o3.stride(0) if b > 1 else hd * w * f,
+                                          dis_bordered.shape[0], b, hs, hd, w, row_off, f, f, n_src * f, f, o3.stride(0) if b > 1 else hd * w * f,
                                           code, _ptr(bias32), _lib.EPI_RELU if relu else 0, slab, tile_w,
                                           _stream()), "gwen_grid_stencil_fwd")
     return out
@@ -173,14 +197,14 @@ def gcn_fused(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor, bias: Opti
     b, n, k = x3.shape
     h, w = graph.grid_shape
     n_out = weight.shape[0]
-    wt = weight.detach().to(x3.dtype).contiguous()
+    wt = _cast_cached(weight, x3.dtype)
     bias32 = _bias32(bias)
     dpad = graph.dis_padded()
     with torch.cuda.device(x3.device):
         if out is None:
             out = torch.empty((b, n, n_out), dtype=x3.dtype, device=x3.device)
         assert out.is_contiguous()
-        check(lib().gwen_gcn_fused_fwd(_ptr(x3), _ptr(wt), _ptr(out), _ptr(dpad), dpad.shape[1], b, h, w, k,
+        check(lib().gwen_gcn_fused_fwd(_ptr(x3), _ptr(wt), _ptr(out), _ptr(dpad), dpad.shape[1], dpad.shape[0], b, h, w, k,
                                        n_out, dtype_code(x3.dtype), _ptr(bias32),
                                        _lib.EPI_RELU if relu else 0, _stream()), "gwen_gcn_fused_fwd")
     return out.reshape(tuple(lead) + (n, n_out))
@@ -197,7 +221,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     n_out = weight.shape[0]
     if weight.shape[1] != k:
         raise ValueError("weight is %s, x has %d features" % (tuple(weight.shape), k))
-    wt = weight.detach().to(x.dtype).contiguous()
+    wt = _cast_cached(weight, x.dtype)
     code = dtype_code(x.dtype)
     bias32 = _bias32(bias)
     if out is not None or not x.is_contiguous():
@@ -250,7 +274,7 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
         dv, ov = _rows_view(dy if dy.is_contiguous() else dy.contiguous()), _rows_view(out)
         if ov is None or ov.shape[:2] != dv.shape[:2] or ov.shape[2] != k or out.dtype != dy.dtype:
             raise ValueError("out must be [..., K] with dense rows matching dy")
-        wt = weight.detach().to(dy.dtype).contiguous()
+        wt = _cast_cached(weight, dy.dtype)
         with torch.cuda.device(dy.device):
             if dy.dtype == torch.float32:     # workspace entry per slice (3xTF32 when it applies)
                 for b in range(dv.shape[0]):
@@ -268,7 +292,7 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
                       "gwen_linear_batched_bwd_data")
         return out
     dy2 = dy.reshape(-1, n_out).contiguous()
-    wt = weight.detach().to(dy2.dtype).contiguous()
+    wt = _cast_cached(weight, dy2.dtype)
     with torch.cuda.device(dy2.device):
         dx = torch.empty((dy2.shape[0], k), dtype=dy2.dtype, device=dy2.device)
         need = C.c_size_t(0)
@@ -282,8 +306,9 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
     return dx.reshape(tuple(dy.shape[:-1]) + (k,))
 
 
-def linear_bwd_weight(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dw[n, k] = sum_m dy[m, n] x[m, k] in fp32 (fixed split order -> deterministic)."""
+def linear_bwd_weight(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[n, k] = sum_m dy[m, n] x[m, k] in fp32 (fixed split order -> deterministic).  ``out``: a
+    contiguous fp32 [n, k] destination (e.g. a slice of a flat gradient bucket)."""
     n_out, k = dy.shape[-1], x.shape[-1]
     dy2 = dy.reshape(-1, n_out).contiguous()
     x2 = x.reshape(-1, k).contiguous()
@@ -292,7 +317,12 @@ def linear_bwd_weight(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         need = C.c_size_t()
         check(lib().gwen_linear_bwd_weight_workspace_bytes(m, k, n_out, C.byref(need)), "wgrad ws")
         ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device)
-        dw = torch.empty((n_out, k), dtype=torch.float32, device=dy2.device)
+        if out is not None:
+            if out.dtype != torch.float32 or tuple(out.shape) != (n_out, k) or not out.is_contiguous():
+                raise ValueError("out must be a contiguous fp32 [%d, %d] tensor" % (n_out, k))
+            dw = out
+        else:
+            dw = torch.empty((n_out, k), dtype=torch.float32, device=dy2.device)
         check(lib().gwen_linear_bwd_weight(_ptr(dy2), _ptr(x2), _ptr(dw), m, k, n_out, n_out, k, k,
                                            dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
               "gwen_linear_bwd_weight")

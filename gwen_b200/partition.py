@@ -353,6 +353,19 @@ class PeerMeshBand(MeshBand):
         dist.barrier(self._group)
         return t
 
+    def error_word(self) -> int:
+        """The protocol's sticky error word (``ctl[5]``, see include/gwen_b200.h): 0 = every halo wait so
+        far completed; bit 0 = a neighbour never announced an epoch within GWEN_PEER_TIMEOUT_MS, bit 1 =
+        a CTA of a launch never published its halo share.  Synchronises the device."""
+        return int(self._ctl[5].item())
+
+    def check(self) -> None:
+        """Raise if a peer launch timed out waiting for a neighbour (results are then undefined)."""
+        e = self.error_word()
+        if e:
+            raise RuntimeError("gwen_b200: peer halo exchange timed out (error word %d): the ranks did not "
+                               "launch the same sequence of peer aggregations, or a neighbour died" % e)
+
     def _peers(self, x3: torch.Tensor):
         from . import _lib
         t, hdl = self._bufs[x3.data_ptr()]
@@ -384,7 +397,7 @@ class PeerMeshBand(MeshBand):
         bias32 = None if bias is None else bias.detach().to(torch.float32).contiguous()
         with torch.cuda.device(x3.device):
             check(lib().gwen_grid_stencil_peer_fwd(
-                x3.data_ptr(), o3.data_ptr(), self.dis.data_ptr(), self.dis.shape[1], b, self.rows, self.W, f,
+                x3.data_ptr(), o3.data_ptr(), self.dis.data_ptr(), self.dis.shape[1], self.dis.shape[0], b, self.rows, self.W, f,
                 x3.stride(0), f, o3.stride(0) if b > 1 else self.n_own * f, ops.dtype_code(x3.dtype),
                 None if bias32 is None else bias32.data_ptr(), _lib.EPI_RELU if relu else 0, 0, 0,
                 C.byref(peers), torch.cuda.current_stream().cuda_stream), "gwen_grid_stencil_peer_fwd")
@@ -428,22 +441,33 @@ class _BandGCNFn(torch.autograd.Function):
             gs = net.buffer(("b", li), b, weight.shape[0], dy.dtype)
         dz, db = ops.relu_bias_bwd(dy, y if ctx.relu else None, ctx.has_bias,
                                    out=None if gs is None else band.owned(gs))
-        if db is not None:
-            db = db.to(weight.dtype)
         need_dx = ctx.needs_input_grad[0]
         dx = None
+        # weight gradient: written straight into this layer's slice of the flat fp32 gradient buffer and
+        # all-reduced from there while the remaining layers' backward runs (net.overlap_grads)
+        if net.overlap_grads and li in net._pending:
+            net._deliver(li)            # an earlier backward's bucket is still in flight: deliver it first
+        wv = net.grad_views(li)[0] if net.overlap_grads else None
         if ctx.agg_first:
-            dw = ops.linear_bwd_weight(dz, saved_in)                  # dW = dz^T (A_hat x)
-            if need_dx:
+            dw = ops.linear_bwd_weight(dz, saved_in, out=wv)          # dW = dz^T (A_hat x)
+        else:
+            dh = band.aggregate(gs)                                   # A_hat^T dz
+            dw = ops.linear_bwd_weight(dh, saved_in, out=wv)          # dW = dh^T x
+        if net.overlap_grads:
+            net.launch_bucket(li, db)
+            dw = db = None              # delivered by allreduce_grads(), already summed over the ranks
+        else:
+            dw = dw.to(weight.dtype)
+            if db is not None:
+                db = db.to(weight.dtype)
+        if need_dx:
+            if ctx.agg_first:
                 gs = net.buffer(("b", li), b, weight.shape[1], dz.dtype)
                 ops.linear_bwd_data(dz, weight, out=band.owned(gs))
                 dx = band.aggregate(gs)
-        else:
-            dh = band.aggregate(gs)                                   # A_hat^T dz
-            dw = ops.linear_bwd_weight(dh, saved_in)                  # dW = dh^T x
-            if need_dx:
+            else:
                 dx = ops.linear_bwd_data(dh, weight)
-        return dx, dw.to(weight.dtype), db, None, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class BandGNNModel(torch.nn.Module):
@@ -451,11 +475,21 @@ class BandGNNModel(torch.nn.Module):
     over the GPUs, ensemble members in the outer batch).  Shares the wrapped model's parameters, so
     ``state_dict`` and optimizers are the plain model's.  ``forward(x_own [B, n_own, C]) -> [B, n_own, C]``;
     after ``backward`` call :meth:`allreduce_grads` (the weight / bias gradients of the ranks are partial
-    sums over their own rows).  Outputs are bitwise equal to the un-partitioned model's rows."""
+    sums over their own rows).  Outputs are bitwise equal to the un-partitioned model's rows.
 
-    def __init__(self, model, band: "PeerMeshBand"):
+    ``overlap_grads`` (default): every layer's backward writes its fp32 ``dW`` / ``db`` into that layer's
+    slice of ONE pre-flattened gradient buffer and starts the NCCL all-reduce of the slice at once, so the
+    reductions of the late layers run under the backward of the early ones; ``allreduce_grads`` then only
+    waits for the handles and hands the (summed) slices to ``p.grad`` -- no ``torch.cat``, no copy-back.
+    With ``overlap_grads=False`` autograd delivers the local gradients and ``allreduce_grads`` reduces
+    them in one flat all-reduce afterwards."""
+
+    def __init__(self, model, band: "PeerMeshBand", overlap_grads: bool = True):
         super().__init__()
-        self.model, self.band = model, band
+        self.model, self.band, self.overlap_grads = model, band, overlap_grads
+        self._flat = None
+        self._views = {}
+        self._pending = {}
         d, u = model.conv_layers.down_conv_layers, model.conv_layers.up_conv_layers
         self.layers = [(d.conv1, True), (d.conv2, True), (d.conv3, True),
                        (u.upconv3, True), (u.upconv4, True), (u.upconv5, False)]
@@ -493,20 +527,68 @@ class BandGNNModel(torch.nn.Module):
 
     def loss(self, y_own: torch.Tensor, target_own: torch.Tensor, mask_own: torch.Tensor) -> torch.Tensor:
         """This rank's share of the reference ``loss_func`` (masked L1, ``models_gnn.py:261-265``) over the
-        WHOLE mesh: local masked mean x (local count / global count), so the shares of all ranks add up
-        to the global masked mean and ``backward`` + :meth:`allreduce_grads` gives its gradient.  The
-        count of masked nodes is all-reduced once per mask and cached."""
+        WHOLE mesh: local masked sum / (B x GLOBAL count x C), so the shares of all ranks add up to the
+        global masked mean and ``backward`` + :meth:`allreduce_grads` gives its gradient.  A band without
+        masked nodes contributes 0 (not 0/0).  The global count is all-reduced once per mask tensor and
+        cached (the cache holds the tensor, so a recycled address cannot alias a stale count)."""
         from .train import masked_l1_loss
-        key = (mask_own.data_ptr(), mask_own._version)
-        if getattr(self, "_mask_key", None) != key:
-            cnt = mask_own.sum().to(torch.float64).reshape(1)
-            tot = cnt.clone()
+        cached = getattr(self, "_mask_cache", None)
+        if cached is None or cached[0] is not mask_own or cached[1] != mask_own._version:
+            tot = mask_own.sum().to(torch.float64).reshape(1)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=self.band.group)
-            self._mask_key, self._mask_share = key, (cnt / tot.clamp_min(1.0)).to(torch.float32)
-        return masked_l1_loss(y_own, target_own, mask_own) * self._mask_share[0]
+            self._mask_cache = (mask_own, mask_own._version, tot.to(torch.float32))
+        return masked_l1_loss(y_own, target_own, mask_own, count=self._mask_cache[2])
+
+    # -- flat gradient buffer: [dW_0 | db_0 | dW_1 | db_1 | ...] in fp32, one bucket per live layer ------
+    def grad_views(self, li: int):
+        """(dW view [out, in], db view [out] or None, bucket view) of layer ``li`` in the flat buffer."""
+        if self._flat is None:
+            dev = self.band.dis.device
+            sizes = [c.lin.weight.numel() + (c.bias.numel() if c.bias is not None else 0) for c, _ in self.layers]
+            self._flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
+            for i, (c, _) in enumerate(self.layers):
+                nw = c.lin.weight.numel()
+                wv = self._flat[off:off + nw].view_as(c.lin.weight)
+                bv = self._flat[off + nw:off + sizes[i]] if c.bias is not None else None
+                self._views[i] = (wv, bv, self._flat[off:off + sizes[i]])
+                off += sizes[i]
+        return self._views[li]
+
+    def launch_bucket(self, li: int, db) -> None:
+        """Called from layer ``li``'s backward once its dW sits in the flat buffer: add db, start the
+        asynchronous all-reduce of the bucket (NCCL's stream waits for the current stream's work so far;
+        the current stream goes on with the next layer's backward)."""
+        wv, bv, bucket = self.grad_views(li)
+        if bv is not None:
+            if db is not None:
+                bv.copy_(db)
+            else:
+                bv.zero_()
+        self._pending[li] = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.band.group, async_op=True)
+
+    def _deliver(self, li: int) -> None:
+        """Wait for layer ``li``'s bucket and add it to the parameters' ``.grad``."""
+        work = self._pending.pop(li, None)
+        if work is None:
+            return
+        work.wait()
+        conv = self.layers[li][0]
+        wv, bv, _ = self._views[li]
+        for p, v in ((conv.lin.weight, wv), (conv.bias, bv)):
+            if p is None or v is None or not p.requires_grad:
+                continue
+            g = v.to(p.dtype, copy=True)
+            p.grad = g if p.grad is None else p.grad.add_(g)
 
     def allreduce_grads(self) -> None:
-        """Sum the parameter gradients over the ranks (one flat NCCL all-reduce)."""
+        """Make ``p.grad`` the gradient summed over the ranks.  ``overlap_grads``: the per-layer
+        all-reduces were started inside backward; wait for them and deliver the slices.  Otherwise: one
+        flat NCCL all-reduce of the local gradients autograd delivered."""
+        if self.overlap_grads:
+            for li in sorted(self._pending, reverse=True):   # completion order: last layer first
+                self._deliver(li)
+            return
         grads = [p.grad for p in self.model.parameters() if p.grad is not None]
         if not grads:
             return

@@ -19,7 +19,7 @@ __all__ = ["masked_l1_loss", "train_step", "eval_step", "gather_eval_results"]
 
 class _MaskedL1(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, output, target, mask):
+    def forward(ctx, output, target, mask, count=None):
         if not output.is_cuda:
             raise RuntimeError("gwen_b200.masked_l1_loss runs on CUDA tensors only (no CPU fallback)")
         y = output.contiguous()
@@ -34,7 +34,9 @@ class _MaskedL1(torch.autograd.Function):
             check(lib().gwen_masked_l1_workspace_bytes(n, C.byref(need)), "masked_l1 ws")
             ws = torch.empty(need.value, dtype=torch.uint8, device=y.device)
             ls = torch.empty(2, dtype=torch.float32, device=y.device)
+            cnt = None if count is None else count.detach().to(device=y.device, dtype=torch.float32).reshape(1).contiguous()
             check(lib().gwen_masked_l1_fwd(y.data_ptr(), t.data_ptr(), m.data_ptr(), b, n, f, dtype_code(y.dtype),
+                                           None if cnt is None else cnt.data_ptr(),
                                            ls.data_ptr(), ws.data_ptr(), need.value,
                                            torch.cuda.current_stream().cuda_stream), "gwen_masked_l1_fwd")
         ctx.save_for_backward(y, t, m, ls)
@@ -51,14 +53,17 @@ class _MaskedL1(torch.autograd.Function):
             check(lib().gwen_masked_l1_bwd(y.data_ptr(), t.data_ptr(), m.data_ptr(), ls.data_ptr(), g.data_ptr(),
                                            b, n, f, dtype_code(y.dtype), dy.data_ptr(),
                                            torch.cuda.current_stream().cuda_stream), "gwen_masked_l1_bwd")
-        return dy, None, None
+        return dy, None, None, None
 
 
-def masked_l1_loss(output: torch.Tensor, target: torch.Tensor, target_mask: torch.Tensor) -> torch.Tensor:
+def masked_l1_loss(output: torch.Tensor, target: torch.Tensor, target_mask: torch.Tensor,
+                   count: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``loss_func(output, target, target_mask)`` of the reference (``models_gnn.py:261-265``) =
     ``L1Loss()(output[target_mask], target[target_mask])`` for ``output [..., N, C]`` and a boolean
-    ``target_mask [N]``, computed without boolean-mask indexing (no host synchronisation)."""
-    return _MaskedL1.apply(output, target, target_mask)
+    ``target_mask [N]``, computed without boolean-mask indexing (no host synchronisation).
+    ``count`` (device scalar): divide by this many masked nodes instead of ``target_mask.sum()`` -- a
+    rank of a partitioned mesh passes the global count and gets its share of the global loss."""
+    return _MaskedL1.apply(output, target, target_mask, count)
 
 
 def train_step(model, node_features: torch.Tensor, edge_index, target_mask: torch.Tensor,
@@ -96,10 +101,13 @@ def gather_eval_results(avg_loss: torch.Tensor, y_preds: List[torch.Tensor], gro
     """The collective tail of ``eval_gnn_with_configs`` (``models_gnn.py:452-489``): every rank
     contributes its average loss and its list of kept predictions; rank 0 returns
     ``(mean of the ranks' losses, predictions concatenated in rank order)``, the other ranks ``None``.
+    Shapes follow the reference literally: ``torch.cat(y_preds)`` (``:465``) of the kept ``output[1]``
+    rows -- 1-D ``[C]`` each for ``output [N, C]`` -- is the 1-D ``[T * C]`` tensor, and the rank-ordered
+    ``torch.cat`` (``:482``) returns ``[world * T * C]``.
     The reference all_gathers the rank ids next to the predictions and sorts by them; ``all_gather``
     already returns rank order, so the sort is the identity and is not repeated here."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    y = torch.cat([p.reshape(1, -1) if p.dim() == 1 else p for p in y_preds]) if y_preds else avg_loss.new_zeros(0)
+    y = torch.cat(list(y_preds)) if y_preds else avg_loss.new_zeros(0)
     ys = [torch.zeros_like(y) for _ in range(world)]
     dist.all_gather(ys, y.contiguous(), group=group)
     losses = [torch.zeros_like(avg_loss) for _ in range(world)]

@@ -186,7 +186,8 @@ int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const void* x, voi
  * with r' = r + row_off and nodes outside [0, hs) x [0, w) contributing 0.  Evaluated as a
  * separable box filter (column sums in registers), sources staged by one 4-D TMA box per tile.
  *   x   : [B, hs, w, F] (node pitch ldx, batch stride x_bstride)      out : [B, hd, w, F]
- *   dis_padded : fp32 [>= round_up(hd, 8) + row_off + 2, dis_pitch] with a one-element ZERO
+ *   dis_padded : fp32 [dis_rows >= round_up(hd, 8) + row_off + 2, dis_pitch] (checked: the kernel
+ *                bulk-copies 10 dis rows per 8-row tile, GWEN_E_BADARG if they would not fit) with a one-element ZERO
  *                border (and zero padding): element [r+1][c+1] = dis[r][c]; dis_pitch % 4 == 0 and >= (ceil(w / tile_w) - 1) * tile_w +
  *                round_up(tile_w + 2, 4); 16-byte aligned (rows are fetched with bulk copies)
  *   row_off    : source row of destination row 0 (0 for a whole mesh; 1 for a row band whose x
@@ -194,7 +195,7 @@ int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan_host, const void* x, voi
  * Agrees with gwen_aggregate_fwd to fp32 rounding (different summation order), deterministic,
  * independent of tiling and partitioning. */
 int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded, int64_t dis_pitch,
-                          int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
+                          int64_t dis_rows, int64_t batch, int64_t hs, int64_t hd, int64_t w, int64_t row_off,
                           int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo,
                           int64_t o_bstride, int dtype, const float* bias, int epilogue,
                           int32_t slab_elems, int32_t tile_w, void* stream);
@@ -217,7 +218,14 @@ int gwen_grid_stencil_fwd(const void* x, void* out, const float* dis_padded, int
  * up_flag/down_flag : address (peer memory) of the neighbour's ctl[1] / ctl[0]
  * ctl               : >= 8 zero-initialised uint32 in LOCAL device memory, owned by the protocol:
  *                     [0] epoch announced by the up neighbour, [1] by the down neighbour,
- *                     [2] epochs completed, [3] CTAs that published their halo share, [4] CTAs done */
+ *                     [2] epochs completed, [3] CTAs that published their halo share, [4] CTAs done,
+ *                     [5] STICKY ERROR word: every wait of the protocol is bounded (GWEN_PEER_TIMEOUT_MS,
+ *                     default 10 s); on expiry bit 0 (a neighbour never announced this epoch: it launched a
+ *                     different sequence of peer calls, or died) or bit 1 (a CTA of this grid never published
+ *                     its halo share) is set and the kernel finishes with undefined halo-dependent rows
+ *                     instead of hanging the GPU.  The host reads it when it next synchronises.
+ * The launch is cooperative (cudaLaunchAttributeCooperative) with the grid clamped to the occupancy
+ * limit, so all CTAs are co-resident or the launch fails with GWEN_E_CUDA. */
 typedef struct gwen_halo_peers {
   const void* up_row;
   const void* down_row;
@@ -227,7 +235,7 @@ typedef struct gwen_halo_peers {
   uint32_t* ctl;
 } gwen_halo_peers;
 int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded, int64_t dis_pitch,
-                               int64_t batch, int64_t hd, int64_t w, int64_t feat,
+                               int64_t dis_rows, int64_t batch, int64_t hd, int64_t w, int64_t feat,
                                int64_t x_bstride, int64_t ldo, int64_t o_bstride, int dtype,
                                const float* bias, int epilogue, int32_t slab_elems, int32_t tile_w,
                                const gwen_halo_peers* peers, void* stream);
@@ -240,10 +248,10 @@ int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded, int6
  * the projection is the CTA-pair GEMM of gwen_linear_fwd.  The aggregated intermediate is rounded to
  * bf16 exactly as the two-kernel path stores it, so results match that path.
  *   x : bf16 [B, h*w, k_in] contiguous      weight : bf16 [n_out, k_in]      y : bf16 [B, h*w, n_out]
- *   dis_padded / dis_pitch : as for gwen_grid_stencil_fwd
+ *   dis_padded / dis_pitch / dis_rows : as for gwen_grid_stencil_fwd (dis_rows >= round_up(h, 8) + 2)
  *   k_in in {64, 128, 192, 256}, n_out % 128 == 0 (else GWEN_E_NOSUPPORT: use the two kernels) */
 int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* dis_padded,
-                       int64_t dis_pitch, int64_t batch, int64_t h, int64_t w, int64_t k_in,
+                       int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t h, int64_t w, int64_t k_in,
                        int64_t n_out, int dtype, const float* bias, int epilogue, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -317,11 +325,15 @@ int gwen_relu_bias_bwd(const void* y, const void* dy, void* dz, float* db, int64
  *   y, target : [batch, n, feat] contiguous;  mask : uint8 [n] (torch.bool), shared by the batch
  *   loss_and_scale : float[2] device: [0] = mean |y - target| over the masked rows (NaN if the mask
  *                    is empty, like torch), [1] = 1 / (batch * count * feat), read by the backward
- *   dloss : device scalar gradient of the loss (NULL = 1);  dy = sign(y - target) * mask * dloss * scale */
+ *   dloss : device scalar gradient of the loss (NULL = 1);  dy = sign(y - target) * mask * dloss * scale
+ *   count_override : NULL, or a device float holding the number of masked nodes to divide by instead
+ *                    of this call's own count -- a rank of a partitioned mesh passes the GLOBAL count, so
+ *                    its value is its share  local_sum / (batch * global_count * feat)  of the loss over
+ *                    the whole mesh (0, not NaN, for a band without masked nodes) */
 int gwen_masked_l1_workspace_bytes(int64_t n, size_t* bytes_out_host);
 int gwen_masked_l1_fwd(const void* y, const void* target, const uint8_t* mask, int64_t batch, int64_t n,
-                       int64_t feat, int dtype, float* loss_and_scale, void* ws, size_t ws_bytes,
-                       void* stream);
+                       int64_t feat, int dtype, const float* count_override, float* loss_and_scale,
+                       void* ws, size_t ws_bytes, void* stream);
 int gwen_masked_l1_bwd(const void* y, const void* target, const uint8_t* mask,
                        const float* loss_and_scale, const float* dloss, int64_t batch, int64_t n,
                        int64_t feat, int dtype, void* dy, void* stream);

@@ -130,16 +130,26 @@ def exact_dis(deg: torch.Tensor) -> torch.Tensor:
 
 
 def gcn_norm(edge_index: torch.Tensor, num_nodes: int, dtype=torch.float32,
-             dis_mode: str = "torch") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+             dis_mode: str = "torch", improved: bool = False
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """A.3: returns (edge_index', edge_weight, dis).
 
     ``dis_mode="torch"`` is the literal PyG sequence ``deg.pow(-0.5)`` in ``dtype``;
     ``"exact"`` rounds the fp64 value once to fp32 (what the CUDA preprocessor emits;
     the two differ by at most 1 ulp, asserted in tests/test_oracle.py).
+    ``improved=True`` (``GCNConv(improved=True)``, not used by GWEN): the appended self loops
+    weigh ``fill_value = 2``, except at nodes whose self loop was already in the input --
+    PyG's ``add_remaining_self_loops`` keeps an existing loop's weight
+    (``loop_attr[edge_index[0][inv_mask]] = edge_attr[inv_mask]``), which is 1 here.
     """
     ei = add_remaining_self_loops(edge_index, num_nodes)
     row, col = ei[0], ei[1]
     ew = torch.ones(ei.size(1), dtype=dtype)
+    if improved:
+        loop_w = torch.full((num_nodes,), 2.0, dtype=dtype)
+        inv = edge_index[0] == edge_index[1]
+        loop_w[edge_index[0][inv]] = 1.0
+        ew[ei.size(1) - num_nodes:] = loop_w
     deg = torch.zeros(num_nodes, dtype=dtype).scatter_add_(0, col, ew)
     if dis_mode == "torch":
         dis = deg.pow(-0.5)

@@ -142,8 +142,10 @@ def _eval_gather_worker(rank, world, port):
     if rank == 0:
         loss, y = res
         assert abs(loss - sum(range(1, world + 1)) / world) < 1e-6
-        want = torch.cat([torch.full((1, 5), float(10 * r + i)) for r in range(world) for i in range(2)])
-        assert torch.equal(y, want)
+        # reference shapes (models_gnn.py:449,465,482): output[1] is 1-D [C], torch.cat(y_preds) is 1-D
+        # [T * C], the rank-ordered cat is 1-D [world * T * C]
+        want = torch.cat([torch.full((5,), float(10 * r + i)) for r in range(world) for i in range(2)])
+        assert y.shape == (world * 2 * 5,) and torch.equal(y, want)
     else:
         assert res is None
     dist.barrier()
