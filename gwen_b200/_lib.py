@@ -15,12 +15,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
 GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4
 EPI_NONE, EPI_RELU = 0, 1
+GWEN_E_NOSUPPORT = -5
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list:
@@ -99,7 +100,7 @@ PROTOTYPES = {
                                      _i64, _i64, _int, _p, _int, _i32, _i32, _p]),
     "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                           _int, _p, _int, _i32, _i32, C.POINTER(HaloPeersStruct), _p]),
-    "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
+    "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _int, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_fwd_workspace_bytes": (_int, [_i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "gwen_linear_fwd_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _sz, _p]),
@@ -122,6 +123,12 @@ PROTOTYPES = {
     "gwen_masked_l1_bwd": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p]),
     "gwen_rows_gather": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_rows_scatter": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+    "gwen_neighbor_workspace_bytes": (_int, [_i64, _i64, C.POINTER(_sz)]),
+    "gwen_neighbor_sample_full": (_int, [_p, _p, _p, _i64, _i64, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "gwen_neighbor_complete": (_int, [_i64, _i64, _i64, _p, _p, _p, _p]),
+    "gwen_gather_rows_bytes": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
+    "gwen_mesh_mask_detect": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
+    "gwen_rows_self_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
 }
 
 _lib = None

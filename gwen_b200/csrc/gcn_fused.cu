@@ -26,9 +26,16 @@
 //   warps 11..18     epilogue: tcgen05.ld -> bias -> bf16 -> ReLU -> 64B-swizzled st.shared -> one 4-D
 //                    TMA store {32 cols, 16, 2, 1} per warp and 32-column sub-chunk (the store clips
 //                    tiles that overhang the mesh).
-// Two resident A buffers (k_in <= 256): the stencil of item t+1 fills one while the MMAs of item t read
-// the other.  (With a single buffer -- all that fits at k_in = 512 -- the stencil and the MMAs of
-// consecutive items serialise and the kernel loses to the two-kernel path: measured 1.44 vs 1.17 ms.)
+// A operand: 8 resident K blocks of 16 KB.  k_in <= 256: two buffers of k_blocks blocks, the stencil of item
+// t+1 fills one while the MMAs of item t read the other.  k_in = 320 .. 512: ONE buffer; every block is
+// released (tcgen05.commit -> a_empty[kb]) as soon as the LAST N tile's MMAs on it have retired, so the stencil
+// of item t+1 refills the blocks behind the MMAs of item t's last N pass.
+// Round 2: (1) the source producer issues a TMA L2 PREFETCH of a later item's boxes (ncu, round 1: the stencil
+// warps spent 35 % of their time on src_full -- with one stage per stencil group the HBM latency of every box
+// was exposed; a prefetched box arrives from L2); (2) the stencil warps can finish the PREVIOUS layer on the
+// aggregated row -- a = relu(A_hat p + pre_bias), rounded to bf16 exactly as k_grid_stencil stores it -- so a
+// layer that aggregates last can hand its un-aggregated projection p straight to the next layer's fused
+// kernel:  Y = epi( relu(A_hat P + b_prev) W^T + b ), and the aggregated tensor of that layer never exists in HBM.
 #include <algorithm>
 #include <cstdlib>
 
@@ -43,7 +50,7 @@ using namespace st;
 namespace {
 
 constexpr int kFusedThreads = 19 * 32;
-constexpr int kMaxKb = 4;      // K <= 256: two resident A buffers of k_blocks x 16 KB each
+constexpr int kMaxKb = 8;      // resident A blocks of 16 KB: two buffers for K <= 256, one for K <= 512
 constexpr int kMaxSB = 6;      // W stage ring
 constexpr int FT_W = 16;       // tile width (destinations), TH = 8 rows -> 128 A rows
 constexpr uint32_t kSrcRow = (FT_W + 2) * 128u;                  // one staged mesh row of a slab
@@ -58,6 +65,11 @@ struct FusedArgs {
   int64_t disb_pitch;
   int batch, h, w, k_blocks, n, bn, sb, relu;
   int tiles_y, pairs_x;
+  int nbuf;                 // resident A buffers: 2 (k_blocks <= 4) or 1
+  const float* pre_bias;    // [k_in] added to the aggregated row before it becomes the A operand (nullable)
+  int pre_relu;             // ReLU on the aggregated row (after pre_bias)
+  int prefetch;             // L2 prefetch distance of the source boxes, in items (0 = off)
+  int epi_groups;           // epilogue warp groups (of 4 warps) that work: 2, or 1 when the A blocks fill the SM
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
@@ -72,7 +84,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     k_gcn_fused(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                 const __grid_constant__ CUtensorMap ymap, FusedArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t src_full[2], src_empty[2], a_full[2 * kMaxKb], a_empty[2 * kMaxKb],
+  __shared__ __align__(8) uint64_t src_full[2], src_empty[2], a_full[kMaxKb], a_empty[kMaxKb],
       b_full[kMaxSB], b_empty[kMaxSB], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -80,13 +92,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   const bool leader = rank == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // shared-memory carve-up
-  const uint32_t a_base = base;                                            // 2 buffers x k_blocks x 16 KB
+  const uint32_t a_base = base;                                            // nbuf buffers x k_blocks x 16 KB
   const uint32_t a_buf_bytes = uint32_t(g.k_blocks) * kABlock;
-  const uint32_t src_base = a_base + 2u * a_buf_bytes;                     // 2 x 24 KB
+  const uint32_t src_base = a_base + uint32_t(g.nbuf) * a_buf_bytes;       // 2 x 24 KB
+  const uint32_t nbuf = uint32_t(g.nbuf);
+  const int kbs = g.k_blocks;                                              // barrier index = abuf * kbs + kb
   const uint32_t b_bytes = uint32_t(g.bn / 2) * 128u;
   const uint32_t b_base = src_base + 2u * kSrcStage;                       // sb x b_bytes
   const uint32_t epi_base = b_base + uint32_t(g.sb) * b_bytes;             // 8 warps x 2 KB
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)) + 8u * 2048u);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)) + uint32_t(4 * g.epi_groups) * 2048u);
 
   const int n_tiles = g.n / g.bn;
   const int n_sub = g.bn / 32;
@@ -111,9 +125,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       mbar_init(smem_u32(&src_full[i]), 1);
       mbar_init(smem_u32(&src_empty[i]), 4);           // the 4 warps of stencil group i
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 2u * 4u * uint32_t(n_sub < 2 ? n_sub : 2));
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 2u * 4u * uint32_t(n_sub < g.epi_groups ? n_sub : g.epi_groups));
     }
-    for (int i = 0; i < 2 * kMaxKb; ++i) {             // [A buffer][K block]
+    for (int i = 0; i < kMaxKb; ++i) {                 // [A buffer][K block]
       mbar_init(smem_u32(&a_full[i]), 8);              // 4 stencil warps x 2 CTAs (leader's is used)
       mbar_init(smem_u32(&a_empty[i]), 1);
     }
@@ -144,6 +158,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       for (int64_t seq = 0; seq < my_items; ++seq) {
         int b, r0, c0;
         item_of(seq, b, r0, c0);
+        if (g.prefetch > 0 && seq + g.prefetch < my_items) {   // pull a later item's boxes into L2 now
+          int pb, pr0, pc0;
+          item_of(seq + g.prefetch, pb, pr0, pc0);
+          for (int kb = 0; kb < g.k_blocks; ++kb)
+            asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(&xmap),
+                         "r"(kb * BK), "r"(pc0 - 1), "r"(pr0 - 1), "r"(pb)
+                         : "memory");
+        }
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           const uint32_t s = uint32_t(kb) & 1u, round = uses[s]++;
           if (round > 0) mbar_wait(smem_u32(&src_empty[s]), (round - 1) & 1u);
@@ -163,14 +185,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       const uint32_t idesc = make_idesc_pair(g.bn);
       uint32_t it_b = 0, seq_n = 0;
       for (int64_t seq = 0; seq < my_items; ++seq) {
-        const uint32_t abuf = uint32_t(seq) & 1u, aphase = uint32_t(seq >> 1) & 1u;
+        const uint32_t abuf = uint32_t(seq % nbuf), aphase = uint32_t(seq / nbuf) & 1u;
         for (int nt = 0; nt < n_tiles; ++nt, ++seq_n) {
           const uint32_t acc = seq_n & 1u, use = seq_n >> 1;
           if (use > 0) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use - 1) & 1u);
           tc_fence_after();
           const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
           for (int kb = 0; kb < g.k_blocks; ++kb, ++it_b) {
-            if (nt == 0) mbar_wait(smem_u32(&a_full[abuf * kMaxKb + kb]), aphase);
+            if (nt == 0) mbar_wait(smem_u32(&a_full[abuf * kbs + kb]), aphase);
             const uint32_t s = it_b % uint32_t(g.sb);
             mbar_wait(smem_u32(&b_full[s]), (it_b / uint32_t(g.sb)) & 1u);
             tc_fence_after();
@@ -181,7 +203,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
               umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
                             (kb | kk) ? 1u : 0u);
             umma_commit_pair(smem_u32(&b_empty[s]));
-            if (nt == n_tiles - 1) umma_commit_pair(smem_u32(&a_empty[abuf * kMaxKb + kb]));  // block is free
+            if (nt == n_tiles - 1) umma_commit_pair(smem_u32(&a_empty[abuf * kbs + kb]));  // block is free
           }
           umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
         }
@@ -215,13 +237,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     const uint32_t q0 = ds + uint32_t(tr) * kDisRow + uint32_t(cb) * 4u;
     const uint32_t q1 = q0 + kDisRow, q2 = q1 + kDisRow;
     const int row0 = tr * FT_W + cb;                       // first A row of this unit
+    const bool pre_relu = g.pre_relu != 0;
     uint32_t round = 0;
     for (int64_t seq = 0; seq < my_items; ++seq)
     for (int kb = grp; kb < g.k_blocks; kb += 2, ++round) {
-      const uint32_t abuf = uint32_t(seq) & 1u;
+      const uint32_t abuf = uint32_t(seq % nbuf), use = uint32_t(seq / nbuf);
+      // per-feature bias of the aggregated row (the previous layer's epilogue moved into this producer)
+      uint64_t pb2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        pb2[k] = g.pre_bias ? pk2(__ldg(g.pre_bias + kb * BK + l * 8 + 2 * k), __ldg(g.pre_bias + kb * BK + l * 8 + 2 * k + 1))
+                            : 0ull;
       mbar_wait(smem_u32(&src_full[grp]), round & 1u);
-      // this A block fed item seq - 2: wait until the MMAs of its last N tile have retired
-      if (seq > 1) mbar_wait(smem_u32(&a_empty[abuf * kMaxKb + kb]), uint32_t((seq >> 1) - 1) & 1u);
+      // this A block fed item seq - nbuf: wait until the MMAs of its last N tile have retired
+      if (use > 0) mbar_wait(smem_u32(&a_empty[abuf * kbs + kb]), (use - 1u) & 1u);
       const uint32_t a_blk = a_base + abuf * a_buf_bytes + uint32_t(kb) * kABlock;
       uint64_t s0[4], s1[4], s2[4];
       float dmid_prev = 0.0f;
@@ -248,9 +277,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
           const uint64_t dm = pk2(dmid_prev, dmid_prev);
           uint64_t o[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) o[k] = mul2(dm, add2(add2(s0[k], s1[k]), s2[k]));
+          for (int k = 0; k < 4; ++k) o[k] = fma2(dm, add2(add2(s0[k], s1[k]), s2[k]), pb2[k]);
           const uint32_t i = uint32_t(row0 + tt - 2);
-          sts_v4(a_blk + i * 128u + ((uint32_t(l) ^ (i & 7u)) << 4), V16<__nv_bfloat16>::pack2(o, false));
+          sts_v4(a_blk + i * 128u + ((uint32_t(l) ^ (i & 7u)) << 4), V16<__nv_bfloat16>::pack2(o, pre_relu));
         }
         dmid_prev = d1;
       }
@@ -258,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(smem_u32(&src_empty[grp]));
-        mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[abuf * kMaxKb + kb]), 0));
+        mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[abuf * kbs + kb]), 0));
       }
     }
   } else {
@@ -271,7 +300,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     uint32_t seq_n = 0;
-    if (g2 < n_sub) {
+    if (g2 < n_sub && g2 < g.epi_groups) {
       for (int64_t seq = 0; seq < my_items; ++seq) {
         int b, r0, c0;
         item_of(seq, b, r0, c0);
@@ -281,13 +310,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
           mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq_n >> 1) & 1u);
           tc_fence_after();
           const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
-          for (int sc = g2; sc < n_sub; sc += 2) {
+          for (int sc = g2; sc < n_sub; sc += g.epi_groups) {
             const int c = sc * 32;
             uint32_t r[32];
             tmem_ld32_nowait(t_addr + uint32_t(c), r);
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (sc + 2 >= n_sub) {  // last TMEM read of this N tile by this warp
+            if (sc + g.epi_groups >= n_sub) {  // last TMEM read of this N tile by this warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_cluster(acc ? empty_remote1 : empty_remote0);
@@ -335,13 +364,13 @@ using namespace gwen;
 extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* dis_padded,
                                   int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t h, int64_t w, int64_t k_in,
                                   int64_t n_out, int dtype, const float* bias, int epilogue,
-                                  void* stream) {
+                                  const float* pre_bias, int pre_epilogue, void* stream) {
   GWEN_CHECK_ARG(batch >= 0 && h >= 0 && w >= 0 && k_in >= 0 && n_out >= 0, "negative size");
   if (batch == 0 || h == 0 || w == 0 || n_out == 0) return GWEN_OK;
   GWEN_CHECK_ARG(x && weight && y && dis_padded, "null pointer");
   if (dtype != GWEN_BF16) return set_err(GWEN_E_NOSUPPORT, "the fused layer kernel is bf16 only");
   if (k_in < 64 || k_in % 64 || k_in > 64 * kMaxKb || n_out % 128 || n_out > 8192)
-    return set_err(GWEN_E_NOSUPPORT, "fused layer needs k_in in {64, 128, 192, 256} and n_out %% 128 == 0");
+    return set_err(GWEN_E_NOSUPPORT, "fused layer needs k_in in {64, 128, .., 512} and n_out %% 128 == 0");
   if (!aligned16(x) || !aligned16(weight) || !aligned16(y) || !aligned16(dis_padded) || dis_pitch % 4)
     return set_err(GWEN_E_ALIGN, "fused layer needs 16-byte aligned tensors");
   if (h * w >= INT32_MAX || batch >= 65536 || sm_count() % 2)
@@ -350,13 +379,26 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   const int tiles_y = static_cast<int>(ceil_div(h, TH)), pairs_x = static_cast<int>(ceil_div(w, 2 * FT_W));
   GWEN_CHECK_ARG(dis_pitch >= int64_t(pairs_x) * 2 * FT_W + 4, "bordered dis pitch too small");
   GWEN_CHECK_ARG(dis_rows >= int64_t(tiles_y) * TH + 2, "bordered dis has too few rows");
-  // N tile: 256 columns unless the resident A block (k_in = 512) leaves no room for 16 KB W stages
-  const size_t fixed = 2 * size_t(k_blocks) * kABlock + 2 * kSrcStage + 8 * 2048 + align_up(size_t(n_out) * 4, 1024) + 1024;
+  // two A buffers while they fit in 8 blocks (k_in <= 256), else one
+  const int nbuf = 2 * k_blocks <= kMaxKb ? 2 : 1;
+  // N tile: 256 columns unless the resident A blocks leave no room for two 16 KB W stages
+  // one working epilogue group (4 staging buffers) when a single A buffer already fills the SM
+  const int epi_groups = nbuf == 2 ? 2 : 1;
+  const size_t fixed = size_t(nbuf) * size_t(k_blocks) * kABlock + 2 * kSrcStage + size_t(4 * epi_groups) * 2048 +
+                       align_up(size_t(n_out) * 4, 1024) + 1024;
   const size_t cap = 226 * 1024;
-  int bn = n_out % 256 == 0 ? 256 : 128;
-  if (fixed + 3 * size_t(bn / 2) * 128 > cap) bn = 128;
+  // N tile: the one that keeps more W bytes in flight (the W ring is what is left of shared memory), 256 on a tie
+  int bn = 0;
+  size_t best = 0;
+  for (int c : {256, 128}) {
+    if (n_out % c) continue;
+    const size_t bb = size_t(c / 2) * 128;
+    if (fixed + 2 * bb > cap) continue;
+    const size_t fl = std::min<size_t>(kMaxSB, (cap - fixed) / bb) * bb;
+    if (fl > best) { best = fl; bn = c; }
+  }
+  if (!bn) return set_err(GWEN_E_NOSUPPORT, "fused layer does not fit in shared memory");
   const size_t b_bytes = size_t(bn / 2) * 128;
-  if (fixed + 2 * b_bytes > cap) return set_err(GWEN_E_NOSUPPORT, "fused layer does not fit in shared memory");
   const int sb = static_cast<int>(std::min<size_t>(kMaxSB, (cap - fixed) / b_bytes));
   auto enc = tensor_map_encoder();
   if (!enc) return set_err(GWEN_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
@@ -384,7 +426,13 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   int rc = make_tensor_map_3d(&wmap, weight, GWEN_BF16, k_in, n_out, 1, k_in, 0, BK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
   FusedArgs g{bias, dis_padded, dis_pitch, static_cast<int>(batch), static_cast<int>(h), static_cast<int>(w),
-              k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x};
+              k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x,
+              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups};
+  static const int prefetch_env = [] {
+    const char* v = getenv("GWEN_FUSED_PREFETCH");
+    return v ? std::max(0, std::min(8, atoi(v))) : 1;
+  }();
+  g.prefetch = prefetch_env;
   const size_t smem = fixed + size_t(sb) * b_bytes;
   GWEN_CUDA(cudaFuncSetAttribute(k_gcn_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t items = batch * tiles_y * pairs_x;

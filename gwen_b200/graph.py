@@ -132,6 +132,11 @@ class GraphCSR:
         self.n_dst, self.n_src, self.num_messages, self.flags = n_dst, n_src, num_messages, flags
         self.edge_index = edge_index
         self.grid_shape = grid_shape
+        # set by build_graph's detection: "plain" (the full H x W mesh), "masked" (mesh minus cut-out
+        # nodes: mesh_valid / masked_idx below), or None (only the node numbering is grid-like, or unknown)
+        self.mesh_kind: Optional[str] = None
+        self.mesh_valid: Optional[torch.Tensor] = None     # bool [N]: node kept in the masked mesh
+        self.masked_idx: Optional[torch.Tensor] = None     # int32 ids of the cut-out nodes
         self._transposed: Optional["GraphCSR"] = None
         self._plans: Dict[Tuple, TilePlan] = {}
         self.order: Optional[torch.Tensor] = None  # locality order for the row kernel
@@ -145,9 +150,24 @@ class GraphCSR:
     def is_plain_mesh(self) -> bool:
         """True when this is exactly the H x W 8-neighbour mesh with default GCN normalisation
         (self loops added, weight 1) over all of its nodes: the stencil kernel applies."""
-        return (self.grid_shape is not None and self.dis is not None and self.n_src == self.n_dst
-                and self.flags == _lib.GRAPH_ADD_SELF_LOOPS
+        return (self.mesh_kind == "plain" and self.grid_shape is not None and self.dis is not None
+                and self.n_src == self.n_dst and self.flags == _lib.GRAPH_ADD_SELF_LOOPS
                 and self.grid_shape[0] * self.grid_shape[1] == self.n_dst)
+
+    @property
+    def is_masked_mesh(self) -> bool:
+        """True for an H x W mesh with cut-out nodes (see csrc/mesh_mask.cu): the stencil kernel applies
+        with dis zeroed at the cut-out nodes, plus one pass over the cut-out rows (out = x)."""
+        return (self.mesh_kind == "masked" and self.mesh_valid is not None and self.dis is not None
+                and self.n_src == self.n_dst and self.flags == _lib.GRAPH_ADD_SELF_LOOPS)
+
+    def dis_padded_masked(self) -> torch.Tensor:
+        """Bordered dis of a masked mesh: dis at valid nodes, 0 at cut-out nodes; cached."""
+        if getattr(self, "_dis_padded_m", None) is None:
+            h, w = self.grid_shape
+            d = torch.where(self.mesh_valid, self.dis, torch.zeros_like(self.dis))
+            self._dis_padded_m = bordered_dis(d.view(h, w))
+        return self._dis_padded_m
 
     def dis_padded(self) -> torch.Tensor:
         """dis with a one-element zero border, [H + 2, pitch] (element [r+1][c+1] = dis[r][c]),
@@ -160,7 +180,7 @@ class GraphCSR:
     # -- backward graph ----------------------------------------------------------------------
     def transposed(self) -> "GraphCSR":
         """CSR of the transposed graph with the SAME per-edge weights (Appendix A.7)."""
-        if self._transposed is None and self.is_plain_mesh:
+        if self._transposed is None and (self.is_plain_mesh or self.is_masked_mesh):
             # the normalised mesh operator is symmetric (undirected edges, w = dis[s] * dis[d]):
             # A_hat^T = A_hat, and the stencil fast path serves the backward pass too
             self._transposed = self
@@ -303,13 +323,59 @@ def _detect_grid(edge_index: torch.Tensor, num_nodes: int) -> Optional[Tuple[int
     return (h, w) if torch.equal(ref, edge_index) else None
 
 
+def _classify_mesh(g: GraphCSR, h: int, w: int) -> Optional[str]:
+    """"plain" / "masked" / None for the CSR ``g`` read as an ``h x w`` mesh (gwen_mesh_mask_detect);
+    fills ``mesh_valid`` / ``masked_idx`` for a masked mesh.  One host sync."""
+    if g.flags != _lib.GRAPH_ADD_SELF_LOOPS or g.n_src != g.n_dst or h * w != g.n_dst or h < 1 or w < 1:
+        return None
+    dev = g.device
+    with torch.cuda.device(dev):
+        valid = torch.empty(g.n_dst, dtype=torch.uint8, device=dev)
+        status = torch.zeros(2, dtype=torch.int32, device=dev)
+        check(lib().gwen_mesh_mask_detect(_ptr(g.rowptr), _ptr(g.src), g.n_dst, h, w, _ptr(valid), _ptr(status),
+                                          _stream()), "gwen_mesh_mask_detect")
+        bad, cut = status.tolist()
+    if bad:
+        return None
+    if cut == 0:
+        return "plain"
+    g.mesh_valid = valid.to(torch.bool)
+    g.masked_idx = torch.nonzero(~g.mesh_valid).flatten().to(torch.int32)
+    return "masked"
+
+
+def _detect_mesh(g: GraphCSR) -> Optional[Tuple[int, int]]:
+    """(H, W) if ``g`` is an 8-neighbour mesh -- complete or with cut-out nodes, edges in ANY order --
+    else None.  The width follows from the largest id difference along an edge (W + 1 as soon as one
+    diagonal edge exists, W when only vertical ones do)."""
+    ei, n = g.edge_index, g.n_dst
+    if ei is None or ei.size(1) == 0 or n < 4 or g.flags != _lib.GRAPH_ADD_SELF_LOOPS:
+        return None
+    d = int((ei[0] - ei[1]).abs().max().item())
+    for w in (d - 1, d):
+        if w >= 2 and n % w == 0 and n // w >= 2:
+            kind = _classify_mesh(g, n // w, w)
+            if kind is not None:
+                g.mesh_kind = kind
+                return (n // w, w)
+    return None
+
+
 def build_graph(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True,
                 improved: bool = False, grid_shape: Optional[Tuple[int, int]] = "auto") -> GraphCSR:
-    """Run the K0 preprocessor.  ``grid_shape`` ("auto" = detect) enables 2-D tile plans."""
+    """Run the K0 preprocessor.  ``grid_shape``: "auto" detects an H x W mesh (PyG ``grid`` order, any other
+    edge order, or a mesh with cut-out nodes: ``GraphCSR.mesh_kind``); an explicit ``(H, W)`` is verified
+    the same way and kept for 2-D tile plans even when the graph is not a mesh operator."""
     flags = (_lib.GRAPH_ADD_SELF_LOOPS if add_self_loops else 0) | (_lib.GRAPH_IMPROVED if improved else 0)
     g = _build(edge_index, num_nodes, flags)
     if grid_shape == "auto":
         grid_shape = _detect_grid(g.edge_index, num_nodes)
+        if grid_shape is not None:
+            g.mesh_kind = "plain" if flags == _lib.GRAPH_ADD_SELF_LOOPS else None
+        else:
+            grid_shape = _detect_mesh(g)
+    elif grid_shape is not None:
+        g.mesh_kind = _classify_mesh(g, int(grid_shape[0]), int(grid_shape[1]))
     g.grid_shape = grid_shape
     return g
 

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import torch
 from torch import nn
 
-from .nn import GCNConv
+from .graph import GraphCSR, get_graph
+from .nn import GCNConv, gcn_conv_pair, pair_fusable
 
 __all__ = ["GNNConfig", "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func"]
 
@@ -45,6 +46,12 @@ class DownConvLayers(nn.Module):
 
     def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
         x = self.conv1(x, edge_index, relu=True)
+        if x.is_cuda and x.dtype == torch.bfloat16:
+            # inference on a large mesh: conv2's aggregation + bias + ReLU run inside conv3's fused kernel
+            # (gwen_b200.nn.gcn_conv_pair, bitwise equal to the two separate layers)
+            graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))
+            if pair_fusable(graph, x, self.conv2, self.conv3):
+                return gcn_conv_pair(x, graph, self.conv2, self.conv3, relu_b=True)
         x = self.conv2(x, edge_index, relu=True)
         x = self.conv3(x, edge_index, relu=True)
         return x

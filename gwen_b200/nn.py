@@ -22,7 +22,7 @@ from torch import Tensor
 from . import ops
 from .graph import GraphCSR, get_graph
 
-__all__ = ["GCNConv", "gcn_conv"]
+__all__ = ["GCNConv", "gcn_conv", "gcn_conv_pair", "pair_fusable"]
 
 
 class _GCNConvFn(torch.autograd.Function):
@@ -78,6 +78,40 @@ def gcn_conv(x: Tensor, graph: GraphCSR, weight: Tensor, bias: Optional[Tensor] 
     if agg_first is None:
         agg_first = weight.shape[1] < weight.shape[0]
     return _GCNConvFn.apply(x, weight, bias, graph, relu, agg_first)
+
+
+# Cross-layer fusion (inference): two consecutive layers  y = epi_b(conv_b(relu(conv_a(x))))  where conv_a
+# aggregates LAST (out <= in):  conv_a(x) = A_hat (x Wa^T) + ba.  Its aggregation, bias and ReLU move into the
+# stencil warps of conv_b's fused kernel, so conv_a is only a GEMM and its aggregated output (the widest tensor
+# of the pair) never exists in HBM:
+#     p  = x Wa^T                                           (tcgen05 GEMM, no epilogue)
+#     q  = relu(A_hat p + ba) Wb^T                          (gwen_gcn_fused_fwd with pre_bias / pre_relu)
+#     y  = epi_b(A_hat q + bb)   if conv_b aggregates last  (mesh stencil)   -- GWEN: conv2 -> conv3
+#     y  = epi_b(q + bb) comes out of the fused kernel's epilogue otherwise.
+# The A operand is rounded to bf16 exactly where the layer-by-layer path stores conv_a's output, so the result
+# is bitwise equal to it.
+import os as _os
+PAIR_FUSION = _os.environ.get("GWEN_PAIR_FUSION", "1") != "0"
+
+
+def pair_fusable(graph: GraphCSR, x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv") -> bool:
+    if not PAIR_FUSION or torch.is_grad_enabled() and (x.requires_grad or conv_a.lin.weight.requires_grad):
+        return False
+    if conv_a.in_channels < conv_a.out_channels or conv_b.in_channels != conv_a.out_channels:
+        return False
+    if conv_a.bias is None:
+        return False
+    return ops.gcn_fused_preferred(graph, x[..., :1].expand(x.shape[:-1] + (conv_a.out_channels,)), conv_b.lin.weight)
+
+
+@torch.no_grad()
+def gcn_conv_pair(x: Tensor, graph: GraphCSR, conv_a: "GCNConv", conv_b: "GCNConv", relu_b: bool) -> Tensor:
+    """``epi_b(conv_b(relu(conv_a(x))))`` with conv_a's aggregation fused into conv_b's kernel (inference)."""
+    p = ops.linear(x, conv_a.lin.weight)
+    b_last = conv_b.in_channels >= conv_b.out_channels
+    q = ops.gcn_fused(graph, p, conv_b.lin.weight, None if b_last else conv_b.bias, False if b_last else relu_b,
+                      pre_bias=conv_a.bias, pre_relu=True)
+    return ops.aggregate(graph, q, conv_b.bias, relu_b) if b_last else q
 
 
 class _Linear(torch.nn.Module):

@@ -25,8 +25,11 @@ _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
 # Which K1 kernel `aggregate` uses:
 #   "rows"    generic CSR kernel (any graph), fp32 bit-exact vs the CPU scatter_add_ order
 #   "tiled"   TMA-staged CSR kernel for mesh graphs, bitwise equal to "rows"
-#   "stencil" separable mesh fast path (plain H x W mesh only), equal to fp32 rounding
-#   "auto"    stencil on a plain mesh with 16-byte rows, else rows
+#   "stencil" separable mesh fast path (plain H x W mesh, or a mesh with cut-out nodes: then one extra
+#             pass rewrites the cut-out rows), equal to fp32 rounding
+#   "auto"    stencil on a plain or masked mesh with 16-byte rows; tiled for any other graph whose nodes
+#             are numbered like a grid (2-D tile plans: improved=True meshes, partition-local graphs)
+#             when the plan fits in shared memory; else rows
 DEFAULT_AGG_KERNEL = "auto"
 
 
@@ -92,12 +95,30 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
     kernel = kernel or DEFAULT_AGG_KERNEL
     esz = x3.element_size()
     if kernel == "auto":
-        kernel = "stencil" if (graph.is_plain_mesh and (f * esz) % 16 == 0) else "rows"
+        if (graph.is_plain_mesh or graph.is_masked_mesh) and (f * esz) % 16 == 0:
+            kernel = "stencil"
+        elif graph.grid_shape is not None and graph.n_src == graph.n_dst and (f * esz) % 16 == 0 and \
+                plan is None and tile_range is None:
+            kernel = "tiled_or_rows"
+        else:
+            kernel = "rows"
     bias32 = _bias32(bias)
     with torch.cuda.device(x3.device):
         if out is None:
             out = torch.empty((b, graph.n_dst, f), dtype=x3.dtype, device=x3.device)
         epi = _lib.EPI_RELU if relu else _lib.EPI_NONE
+        if kernel == "tiled_or_rows":
+            # the TMA-staged kernel (bitwise equal to "rows", ~2x faster on grid-numbered graphs) unless
+            # its stages do not fit in shared memory for this width
+            plan = graph.tile_plan(tile, run_len)
+            rc = lib().gwen_aggregate_tiled_fwd(C.byref(plan.struct), _ptr(x3), _ptr(out), b, n_src, f, f,
+                                                n_src * f, f, graph.n_dst * f, code, _ptr(bias32), epi, slab,
+                                                0, 0, _stream())
+            if rc == _lib.GWEN_E_NOSUPPORT:
+                kernel = "rows"
+            else:
+                check(rc, "gwen_aggregate_tiled_fwd")
+                return out.reshape(tuple(lead) + (graph.n_dst, f))
         if kernel == "tiled":
             if plan is None:
                 plan = graph.tile_plan(tile, run_len)
@@ -108,14 +129,20 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
                                                  tile_range[1] if tile_range else 0,
                                                  _stream()), "gwen_aggregate_tiled_fwd")
         elif kernel == "stencil":
-            if not graph.is_plain_mesh:
-                raise RuntimeError("the stencil kernel needs a plain H x W mesh graph")
+            masked = graph.is_masked_mesh
+            if not (graph.is_plain_mesh or masked):
+                raise RuntimeError("the stencil kernel needs a plain (or masked) H x W mesh graph")
             h, w = graph.grid_shape
-            dpad = graph.dis_padded()
+            dpad = graph.dis_padded_masked() if masked else graph.dis_padded()
             check(lib().gwen_grid_stencil_fwd(_ptr(x3), _ptr(out), _ptr(dpad), dpad.shape[1], dpad.shape[0], b, h, h, w,
                                               0, f, f, n_src * f, f, graph.n_dst * f, code,
                                               _ptr(bias32), epi, slab, tile[0] if tile else 0,
                                               _stream()), "gwen_grid_stencil_fwd")
+            if masked:   # cut-out nodes keep only their self loop: out = epi(x + bias)
+                idx = graph.masked_idx
+                check(lib().gwen_rows_self_fwd(_ptr(x3), _ptr(out), _ptr(idx), idx.numel(), b, f, f, n_src * f, f,
+                                               graph.n_dst * f, code, _ptr(bias32), epi, _stream()),
+                      "gwen_rows_self_fwd")
         elif kernel == "rows":
             check(lib().gwen_aggregate_fwd(_ptr(graph.rowptr), _ptr(graph.src), _ptr(graph.w),
                                            _ptr(graph.order), _ptr(x3), _ptr(out), b, graph.n_dst,
@@ -169,15 +196,16 @@ def _rows_view(t: torch.Tensor):
 # The fused layer kernel pays off once every CTA pair has a long queue of 8 x 32 tiles (measured on
 # 1158 x 774 meshes: -4 % .. -11 % vs the two-kernel path; on 582 x 390 it is slower).
 FUSED_MIN_ITEMS = 3500
+FUSED_MAX_K = 512       # widest input the fused kernel keeps resident (one A buffer above 256)
 
 
 def gcn_fused_supported(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
-    """True when ``gcn_fused`` can serve this layer: plain mesh, bf16, k_in in {64, 128, 192, 256},
+    """True when ``gcn_fused`` can serve this layer: plain mesh, bf16, k_in in {64, 128, .., 512},
     n_out a multiple of 128 (and GWEN_NO_FUSED unset)."""
     import os
     k, n = weight.shape[1], weight.shape[0]
     return (os.environ.get("GWEN_NO_FUSED") is None and graph.is_plain_mesh and x.dtype == torch.bfloat16
-            and x.is_cuda and 64 <= k <= 256 and k % 64 == 0 and n % 128 == 0 and n <= 8192)
+            and x.is_cuda and 64 <= k <= FUSED_MAX_K and k % 64 == 0 and n % 128 == 0 and n <= 8192)
 
 
 def gcn_fused_preferred(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
@@ -190,8 +218,11 @@ def gcn_fused_preferred(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) 
 
 
 def gcn_fused(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-              relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = epi((A_hat x) W^T + bias) in one kernel (gwen_gcn_fused_fwd); x [..., N, K] bf16."""
+              relu: bool = False, out: Optional[torch.Tensor] = None, pre_bias: Optional[torch.Tensor] = None,
+              pre_relu: bool = False) -> torch.Tensor:
+    """y = epi((A_hat x) W^T + bias) in one kernel (gwen_gcn_fused_fwd); x [..., N, K] bf16.
+    ``pre_bias`` / ``pre_relu``: y = epi(pre(A_hat x + pre_bias) W^T + bias) -- the previous layer's bias and
+    ReLU applied to the aggregated row inside the kernel (that layer then only runs its projection)."""
     _require_cuda(x, "x")
     x3, lead = _as_3d(x)
     b, n, k = x3.shape
@@ -199,6 +230,7 @@ def gcn_fused(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor, bias: Opti
     n_out = weight.shape[0]
     wt = _cast_cached(weight, x3.dtype)
     bias32 = _bias32(bias)
+    pre32 = _bias32(pre_bias)
     dpad = graph.dis_padded()
     with torch.cuda.device(x3.device):
         if out is None:
@@ -206,7 +238,8 @@ def gcn_fused(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor, bias: Opti
         assert out.is_contiguous()
         check(lib().gwen_gcn_fused_fwd(_ptr(x3), _ptr(wt), _ptr(out), _ptr(dpad), dpad.shape[1], dpad.shape[0], b, h, w, k,
                                        n_out, dtype_code(x3.dtype), _ptr(bias32),
-                                       _lib.EPI_RELU if relu else 0, _stream()), "gwen_gcn_fused_fwd")
+                                       _lib.EPI_RELU if relu else 0, _ptr(pre32), _lib.EPI_RELU if pre_relu else 0,
+                                       _stream()), "gwen_gcn_fused_fwd")
     return out.reshape(tuple(lead) + (n, n_out))
 
 

@@ -249,10 +249,15 @@ int gwen_grid_stencil_peer_fwd(void* x, void* out, const float* dis_padded, int6
  * bf16 exactly as the two-kernel path stores it, so results match that path.
  *   x : bf16 [B, h*w, k_in] contiguous      weight : bf16 [n_out, k_in]      y : bf16 [B, h*w, n_out]
  *   dis_padded / dis_pitch / dis_rows : as for gwen_grid_stencil_fwd (dis_rows >= round_up(h, 8) + 2)
- *   k_in in {64, 128, 192, 256}, n_out % 128 == 0 (else GWEN_E_NOSUPPORT: use the two kernels) */
+ *   k_in in {64, 128, .., 512}, n_out % 128 == 0 (else GWEN_E_NOSUPPORT: use the two kernels)
+ *   pre_bias fp32 [k_in] (nullable) / pre_epilogue (GWEN_EPI_RELU or 0): applied to the AGGREGATED row before it
+ *   is projected, a = epi_pre(A_hat x + pre_bias) rounded to bf16 as gwen_grid_stencil_fwd would store it --
+ *   the previous layer's bias / ReLU when that layer aggregates last and hands over its un-aggregated
+ *   projection:  y = epi( epi_pre(A_hat x + pre_bias) W^T + bias ). */
 int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* dis_padded,
                        int64_t dis_pitch, int64_t dis_rows, int64_t batch, int64_t h, int64_t w, int64_t k_in,
-                       int64_t n_out, int dtype, const float* bias, int epilogue, void* stream);
+                       int64_t n_out, int dtype, const float* bias, int epilogue, const float* pre_bias,
+                       int pre_epilogue, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
@@ -348,6 +353,54 @@ int gwen_rows_gather(const void* x, const int32_t* idx, void* buf, int64_t batch
                      int64_t feat, int64_t ldx, int64_t x_bstride, int dtype, void* stream);
 int gwen_rows_scatter(const void* buf, const int32_t* idx, void* x, int64_t batch, int64_t n_idx,
                       int64_t feat, int64_t ldx, int64_t x_bstride, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-neighbour subgraph extraction: what
+ * NeighborLoader(data, num_neighbors=[-1] * hops, batch_size, shuffle=False) does on the CPU before every
+ * model call of the reference loops (src/gwen/models_gnn.py:351-356, :434-439) through torch_geometric 2.3.1
+ * -> torch_sparse 0.6.17 neighbor_sample<replace=false, directed=true> (not in the reference tree; contract
+ * restated in oracle/neighbor_oracle.py).
+ *   colptr int32[n + 1], row int32[e] : CSC of the graph (in-neighbours of node w = row[colptr[w] .. colptr[w+1]));
+ *       this is gwen_graph_build with flags = 0 (destination-sorted, stable in edge_index order -- for the
+ *       (row, col)-sorted edge lists the reference builds that is PyG's to_csc order)
+ *   perm int64[e] (nullable) : CSC slot -> position in the caller's edge_index (gwen_graph_build's perm)
+ *   seeds int64[n_seeds] : the batch's input nodes, distinct
+ *   node_out int64[n]   : seeds first, then newly reached nodes in discovery order (n_id)
+ *   row_out / col_out int64[e] : relabelled edge_index of the batch (row = source, col = destination), one edge
+ *       per (frontier node, in-neighbour) in visiting order;  edge_out int64[e] : e_id (perm[slot], or the slot)
+ *   counts_out int32[3] device : {nodes, edges, bad seeds (out of range or repeated)}
+ * Nothing synchronises the host; the caller reads counts_out when it needs the sizes. */
+int gwen_neighbor_workspace_bytes(int64_t n, int64_t e, size_t* bytes_out_host);
+int gwen_neighbor_sample_full(const int32_t* colptr, const int32_t* row, const int64_t* perm, int64_t n,
+                              int64_t e, const int64_t* seeds, int64_t n_seeds, int32_t hops,
+                              int64_t* node_out, int64_t* row_out, int64_t* col_out, int64_t* edge_out,
+                              int32_t* counts_out, void* ws, size_t ws_bytes, void* stream);
+/* The same for the complete directed graph on n nodes sorted by (row, col) (erdos_renyi_graph(n, 1),
+ * src/gwen/utils.py:176) and seeds seed_start .. seed_start + n_seeds - 1, hops >= 2: closed form, ONE launch.
+ * node_out int64[n]; edge_index_out int64[2, n (n - 1)] (row 0 = source, row 1 = destination);
+ * eid_out int64[n (n - 1)] or NULL. */
+int gwen_neighbor_complete(int64_t n, int64_t seed_start, int64_t n_seeds, int64_t* node_out,
+                           int64_t* edge_index_out, int64_t* eid_out, void* stream);
+/* dst[j, :] = src[idx[j], :] for rows of row_bytes bytes (x[n_id], target_mask[n_id]: the node-attribute
+ * filtering of PyG's filter_data). */
+int gwen_gather_rows_bytes(const void* src, const int64_t* idx, void* dst, int64_t rows, int64_t row_bytes,
+                           int64_t src_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Masked meshes (an H x W 8-neighbour mesh with a set of nodes cut out: land/sea masks, non-rectangular
+ * domains).  A cut-out node keeps only the self loop GCN normalisation adds (out = x); a valid node's
+ * degree counts its valid neighbours.  With dis zeroed at the cut-out nodes the aggregation of the valid
+ * nodes is gwen_grid_stencil_fwd unchanged, and gwen_rows_self_fwd rewrites the cut-out rows.
+ * gwen_mesh_mask_detect: is the CSR of gwen_graph_build (flags = GWEN_GRAPH_ADD_SELF_LOOPS) such a graph
+ * for this h x w?  valid_out uint8[n] (1 = node has an in-edge besides its self loop);
+ * status int32[2] device: [0] = nodes whose in-neighbour set is NOT exactly {valid mesh neighbours}
+ * (0 means yes), [1] = number of cut-out nodes. */
+int gwen_mesh_mask_detect(const int32_t* rowptr, const int32_t* src, int64_t n, int64_t h, int64_t w,
+                          uint8_t* valid_out, int32_t* status, void* stream);
+/* out[b, idx[j], :] = epi(x[b, idx[j], :] + bias) for the n_idx listed rows (fp32 add, then ReLU). */
+int gwen_rows_self_fwd(const void* x, void* out, const int32_t* idx, int64_t n_idx, int64_t batch,
+                       int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo, int64_t o_bstride,
+                       int dtype, const float* bias, int epilogue, void* stream);
 
 #ifdef __cplusplus
 }

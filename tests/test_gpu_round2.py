@@ -180,3 +180,175 @@ def test_stencil_rejects_short_bordered_dis(dev):
     short = disb[:hs + 2].contiguous()                          # the round-1 size for hs % 8 == 4 minus 2
     with pytest.raises(RuntimeError, match="bordered dis"):
         ops.mesh_stencil(x, short, hs, 1, w, hs - 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# meshes with cut-out nodes, meshes in any edge order, grid-numbered graphs that are not mesh operators
+# ---------------------------------------------------------------------------------------------
+def _masked_mesh(h, w, frac, seed):
+    ei = orc.grid(h, w)
+    g = torch.Generator().manual_seed(seed)
+    cut = torch.rand(h * w, generator=g) < frac
+    keep = ~(cut[ei[0]] | cut[ei[1]])
+    return ei[:, keep], cut
+
+
+@pytest.mark.parametrize("hw,frac", [((9, 8), 0.3), ((40, 70), 0.1), ((17, 23), 0.6), ((64, 7), 0.05)])
+@pytest.mark.parametrize("feat", [64, 36])
+def test_masked_mesh_keeps_the_stencil_path(dev, hw, frac, feat):
+    h, w = hw
+    ei, cut = _masked_mesh(h, w, frac, seed=h + w)
+    n = h * w
+    g = gw.build_graph(ei.to(dev), n)
+    assert g.mesh_kind == "masked" and g.grid_shape == (h, w) and g.is_masked_mesh and not g.is_plain_mesh
+    # a node is "valid" iff it kept an edge (a kept node whose neighbours were all cut behaves like a cut one)
+    deg = torch.zeros(n, dtype=torch.long).scatter_add_(0, ei[1][ei[0] != ei[1]], torch.ones(int((ei[0] != ei[1]).sum()), dtype=torch.long))
+    assert torch.equal(g.mesh_valid.cpu(), deg > 0)
+    x = wts.features((2, n, feat), 3)
+    b = wts.small_bias(feat, 4)
+    ei2, ew, _ = orc.gcn_norm(ei, n, dis_mode="exact")
+    ref = torch.relu(orc.propagate(x, ei2, ew, n) + b)
+    out = ops.aggregate(g, x.to(dev), b.to(dev), relu=True)                      # auto -> stencil + cut-out rows
+    assert nmax(out, ref) <= 1e-6
+    rows = ops.aggregate(g, x.to(dev), b.to(dev), relu=True, kernel="rows")       # bit-exact CSR kernel
+    assert torch.equal(rows.cpu(), ref)
+    assert nmax(out, rows) <= 1e-6
+    cut_rows = (~g.mesh_valid).nonzero().flatten()
+    assert torch.equal(out[:, cut_rows].cpu(), torch.relu(x[:, cut_rows.cpu()] + b))   # out = x (+ bias) exactly
+    xb = x.to(dev).bfloat16()
+    outb = ops.aggregate(g, xb, b.to(dev), relu=True)
+    refb = torch.relu(orc.propagate(xb.float().cpu(), ei2, ew, n) + b)
+    assert torch.all((outb.float().cpu() - refb).abs() <= refb.abs() * 2.0 ** -7 + 1e-6)
+    assert g.transposed() is g                                                   # the operator is symmetric
+
+
+def test_masked_mesh_layer_forward_backward(dev):
+    h, w, fi, fo = 20, 31, 24, 40
+    ei, _ = _masked_mesh(h, w, 0.15, seed=9)
+    n = h * w
+    x, wt, b = wts.features((n, fi), 1), wts.glorot(fo, fi, 2), wts.small_bias(fo, 3)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.relu(orc.gcn_conv_forward(xr, ei, wr, br))
+    yr.square().sum().backward()
+    g = gw.build_graph(ei.to(dev), n)
+    assert g.is_masked_mesh
+    for agg_first in (False, True):
+        xd, wd, bd = (t.to(dev).requires_grad_(True) for t in (x, wt, b))
+        y = gw.gcn_conv(xd, g, wd, bd, relu=True, agg_first=agg_first)
+        assert nmax(y, yr) <= 1e-5
+        y.square().sum().backward()
+        assert nmax(xd.grad, xr.grad) <= 1e-4 and nmax(wd.grad, wr.grad) <= 1e-4 and nmax(bd.grad, br.grad) <= 1e-4
+    # the drop-in layer finds the masked mesh by itself from a raw edge_index
+    conv = gw.GCNConv(fi, fo).to(dev)
+    with torch.no_grad():
+        conv.lin.weight.copy_(wt)
+        conv.bias.copy_(b)
+        assert nmax(conv(x.to(dev), ei.to(dev), relu=True), yr) <= 1e-5
+    assert gw.get_graph(ei.to(dev), n).mesh_kind in ("masked", None)   # a different tensor: rebuilt, same answer
+    gw.clear_graph_cache()
+
+
+def test_mesh_in_any_edge_order_is_detected(dev):
+    h, w = 13, 21
+    ei = orc.grid(h, w)
+    perm = torch.randperm(ei.size(1), generator=torch.Generator().manual_seed(2))
+    g = gw.build_graph(ei[:, perm].to(dev), h * w)
+    assert g.mesh_kind == "plain" and g.grid_shape == (h, w) and g.is_plain_mesh
+    x = wts.features((h * w, 32), 5)
+    ref = ops.aggregate(gw.build_graph(ei.to(dev), h * w), x.to(dev), kernel="stencil")
+    assert torch.equal(ops.aggregate(g, x.to(dev)), ref)             # same operator, same kernel
+    # a duplicate edge, a missing edge, a non-neighbour edge: not a mesh operator
+    for bad in (torch.cat([ei, ei[:, 5:6]], 1), ei[:, 1:], torch.cat([ei, torch.tensor([[0], [h * w - 1]])], 1)):
+        gb = gw.build_graph(bad.to(dev), h * w)
+        assert not gb.is_plain_mesh and not gb.is_masked_mesh
+        xb = x.to(dev)
+        ei2, ew, _ = orc.gcn_norm(bad, h * w, dis_mode="exact")
+        assert torch.equal(ops.aggregate(gb, xb).cpu(), orc.propagate(x, ei2, ew, h * w))
+    # an explicit grid_shape is verified, not trusted
+    gx = gw.build_graph(ei[:, 1:].to(dev), h * w, grid_shape=(h, w))
+    assert gx.grid_shape == (h, w) and gx.mesh_kind is None and not gx.is_plain_mesh
+
+
+def test_auto_prefers_the_tiled_kernel_on_grid_numbered_graphs(dev):
+    """improved=True meshes (and any graph with a known grid numbering) run the TMA-staged CSR kernel,
+    bitwise equal to the row kernel, instead of silently dropping to the slow path."""
+    h, w, f = 24, 40, 64
+    ei = orc.grid(h, w)
+    gi = gw.build_graph(ei.to(dev), h * w, improved=True)
+    assert gi.grid_shape == (h, w) and gi.mesh_kind is None
+    x = wts.features((2, h * w, f), 6).to(dev)
+    b = wts.small_bias(f, 7).to(dev)
+    rows = ops.aggregate(gi, x, b, relu=True, kernel="rows")
+    auto = ops.aggregate(gi, x, b, relu=True)
+    assert torch.equal(auto, rows)
+    assert len(gi._plans) == 1                                   # a tile plan was built: the tiled kernel ran
+    ei2, ew, _ = orc.gcn_norm(ei, h * w, dis_mode="exact", improved=True)
+    assert torch.equal(rows.cpu(), torch.relu(orc.propagate(x.cpu(), ei2, ew, h * w) + b.cpu()))
+    # ragged feature width: no 16-byte rows -> row kernel
+    x2 = wts.features((h * w, 6), 8).to(dev)
+    assert torch.equal(ops.aggregate(gi, x2), ops.aggregate(gi, x2, kernel="rows"))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused layer kernel, round 2: k_in up to 512 (one resident A buffer), previous layer's bias + ReLU in the
+# stencil warps, cross-layer pair fusion in the model
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(8, 32), (21, 45), (40, 70)])
+@pytest.mark.parametrize("k,n", [(320, 128), (512, 256), (512, 1024), (384, 512)])
+@pytest.mark.parametrize("batch", [1, 3])
+def test_fused_layer_wide_input_matches_two_kernel_path(dev, hw, k, n, batch):
+    h, w = hw
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    x = wts.features((batch, h * w, k), 51).bfloat16().to(dev)
+    wt, b = wts.glorot(n, k, 52).bfloat16().to(dev), wts.small_bias(n, 53).to(dev)
+    assert ops.gcn_fused_supported(g, x, wt)
+    y = ops.gcn_fused(g, x, wt, b, relu=True)
+    hh = ops.aggregate(g, x, kernel="stencil")
+    assert torch.equal(y, ops.linear(hh, wt, b, relu=True))
+    assert torch.equal(y, ops.gcn_fused(g, x, wt, b, relu=True))                  # deterministic
+    assert torch.equal(ops.gcn_fused(g, x, wt), ops.linear(hh, wt))               # no bias, no relu
+
+
+@pytest.mark.parametrize("hw", [(9, 33), (40, 70)])
+@pytest.mark.parametrize("k,n", [(64, 128), (256, 512), (512, 256)])
+def test_fused_layer_with_previous_layers_epilogue(dev, hw, k, n):
+    """y = epi(relu(A_hat p + b_prev) W^T + b): bitwise equal to stencil(bias, relu) followed by the GEMM."""
+    h, w = hw
+    g = gw.build_graph(gw.grid(h, w, dev), h * w)
+    p = wts.features((2, h * w, k), 61).bfloat16().to(dev)
+    bp = wts.small_bias(k, 62).to(dev)
+    wt, b = wts.glorot(n, k, 63).bfloat16().to(dev), wts.small_bias(n, 64).to(dev)
+    a = ops.aggregate(g, p, bp, relu=True, kernel="stencil")
+    assert torch.equal(ops.gcn_fused(g, p, wt, b, relu=True, pre_bias=bp, pre_relu=True), ops.linear(a, wt, b, relu=True))
+    a2 = ops.aggregate(g, p, bp, relu=False, kernel="stencil")
+    assert torch.equal(ops.gcn_fused(g, p, wt, None, relu=False, pre_bias=bp, pre_relu=False), ops.linear(a2, wt))
+
+
+def test_model_pair_fusion_is_bitwise_equal(dev, monkeypatch):
+    """DownConvLayers runs conv2 -> conv3 as GEMM + fused kernel + stencil under no_grad: same bits as the
+    layer-by-layer path; with grad enabled the layer-by-layer path is used."""
+    from gwen_b200 import nn as gnn
+    monkeypatch.setattr(ops, "FUSED_MIN_ITEMS", 0)
+    h, w, c, hid = 24, 40, 64, 1024
+    n = h * w
+    torch.manual_seed(3)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    model = gw.GNNModel(cfg).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    ei = gw.grid(h, w, dev)
+    x = wts.features((2, n, c), 71).bfloat16().to(dev)
+    with torch.no_grad():
+        y_pair = model(x, ei)
+        monkeypatch.setattr(gnn, "PAIR_FUSION", False)
+        y_seq = model(x, ei)
+        monkeypatch.setattr(gnn, "PAIR_FUSION", True)
+    assert torch.equal(y_pair, y_seq)
+    g = gw.get_graph(ei, n)
+    d = model.conv_layers.down_conv_layers
+    with torch.no_grad():
+        assert gnn.pair_fusable(g, torch.empty(2, n, hid, device=dev, dtype=torch.bfloat16), d.conv2, d.conv3)
+    assert not gnn.pair_fusable(g, torch.empty(2, n, hid, device=dev, dtype=torch.bfloat16), d.conv2, d.conv3)
+    gw.clear_graph_cache()
