@@ -70,6 +70,7 @@ struct FusedArgs {
   int pre_relu;             // ReLU on the aggregated row (after pre_bias)
   int prefetch;             // L2 prefetch distance of the source boxes, in items (0 = off)
   int epi_groups;           // epilogue warp groups (of 4 warps) that work: 2, or 1 when the A blocks fill the SM
+  int epi_bufs;             // 2 KB staging buffers per epilogue warp: 2 = one TMA store in flight while the next packs
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
@@ -100,7 +101,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   const uint32_t b_bytes = uint32_t(g.bn / 2) * 128u;
   const uint32_t b_base = src_base + 2u * kSrcStage;                       // sb x b_bytes
   const uint32_t epi_base = b_base + uint32_t(g.sb) * b_bytes;             // 8 warps x 2 KB
-  float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)) + uint32_t(4 * g.epi_groups) * 2048u);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)) +
+                                           uint32_t(4 * g.epi_groups * g.epi_bufs) * 2048u);
 
   const int n_tiles = g.n / g.bn;
   const int n_sub = g.bn / 32;
@@ -293,7 +295,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   } else {
     // ===== epilogue warps 11..18: TMEM lanes 32 (warp % 4) .. +31 = tile rows 2q, 2q + 1 =====
     const int q = warp & 3, g2 = (warp - 11) >> 2;
-    const uint32_t my_stage = epi_base + uint32_t(warp - 11) * 2048u;
+    const uint32_t my_stage0 = epi_base + uint32_t(warp - 11) * 2048u * uint32_t(g.epi_bufs);
+    uint32_t ebuf = 0;
     const uint32_t row_off = uint32_t(lane) * 64u;
     const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B
     const bool relu = g.relu != 0;
@@ -314,7 +317,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
             const int c = sc * 32;
             uint32_t r[32];
             tmem_ld32_nowait(t_addr + uint32_t(c), r);
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const uint32_t my_stage = my_stage0 + ebuf * 2048u;
+            if (lane == 0) {   // the staging buffer about to be overwritten must have been read by its TMA store
+              if (g.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            ebuf = (ebuf + 1u) & uint32_t(g.epi_bufs - 1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (sc + g.epi_groups >= n_sub) {  // last TMEM read of this N tile by this warp
               tc_fence_before();
@@ -384,7 +392,13 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   // N tile: 256 columns unless the resident A blocks leave no room for two 16 KB W stages
   // one working epilogue group (4 staging buffers) when a single A buffer already fills the SM
   const int epi_groups = nbuf == 2 ? 2 : 1;
-  const size_t fixed = size_t(nbuf) * size_t(k_blocks) * kABlock + 2 * kSrcStage + size_t(4 * epi_groups) * 2048 +
+  // double-buffered epilogue staging when the A blocks leave room (k_in <= 128: the store-bound layers, 64 -> 1024)
+  static const int ebufs_env = [] {
+    const char* v = getenv("GWEN_FUSED_EPI_BUFS");
+    return v ? atoi(v) : 0;
+  }();
+  const int epi_bufs = (ebufs_env == 1 || ebufs_env == 2) ? ebufs_env : (k_blocks <= 2 ? 2 : 1);
+  const size_t fixed = size_t(nbuf) * size_t(k_blocks) * kABlock + 2 * kSrcStage + size_t(4 * epi_groups * epi_bufs) * 2048 +
                        align_up(size_t(n_out) * 4, 1024) + 1024;
   const size_t cap = 226 * 1024;
   // N tile: the one that keeps more W bytes in flight (the W ring is what is left of shared memory), 256 on a tie
@@ -427,10 +441,13 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   if (rc != GWEN_OK) return rc;
   FusedArgs g{bias, dis_padded, dis_pitch, static_cast<int>(batch), static_cast<int>(h), static_cast<int>(w),
               k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x,
-              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups};
+              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs};
   static const int prefetch_env = [] {
     const char* v = getenv("GWEN_FUSED_PREFETCH");
-    return v ? std::max(0, std::min(8, atoi(v))) : 1;
+    // measured at the cfg 3 shapes (round 2, distance 0 / 1 / 2): 512->1024 8.65 / 9.62 / 9.70 ms, 512->256
+    // 4.01 / 3.93 / 4.14, 256->512 and 64->1024 unchanged: the boxes' halos are L2 hits anyway and the extra
+    // requests compete with the W tiles -- off by default
+    return v ? std::max(0, std::min(8, atoi(v))) : 0;
   }();
   g.prefetch = prefetch_env;
   const size_t smem = fixed + size_t(sb) * b_bytes;

@@ -329,13 +329,15 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
     return v ? atoi(v) : 0;
   }();
   const int epi_groups = (groups_env == 2 || groups_env == 4) ? groups_env : (k >= 512 ? 2 : 4);
-  // write-bound shapes (shallow K: all 16 epilogue warps work) store 64-column chunks = 128-byte rows
+  // 64-column chunks (128-byte store rows) only for the narrow output tile (bn = 64: one chunk per warp).  Measured
+  // at M = 896 292 (round 2, 32 / 64 columns): 64->1024 0.359 / 0.416 ms, 256->512 0.283 / 0.342, 1024->64 0.390 / 0.369
+  // -- the wider chunk serialises two TMEM loads per store and costs a ring stage; the store row width was not the limit.
   static const int cols_env = [] {
     const char* v = getenv("GWEN_TC3_EPI_COLS");
     return v ? atoi(v) : 0;
   }();
   const int epi_cols = (cols_env == 32 || cols_env == 64) ? (bn % cols_env ? 32 : cols_env)
-                                                          : (epi_groups == 4 && bn % 64 == 0 ? 64 : 32);
+                                                          : (epi_groups == 4 && bn == 64 ? 64 : 32);
   rc = epi_cols == 64
            ? make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)
            : make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
