@@ -16,8 +16,9 @@ from .host_stream import HostBandPropagator, HostPropagator, pinned_near_gpu
 from .train import eval_step, gather_eval_results, masked_l1_loss, train_step
 from .data import GraphDataset
 from .loader import NeighborLoader
+from . import optim  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["GCNConv", "gcn_conv", "GraphCSR", "build_graph", "get_graph", "clear_graph_cache",
            "grid", "grid_edge_count", "complete_graph", "erdos_renyi_graph", "HostPropagator", "HostBandPropagator", "pinned_near_gpu", "masked_l1_loss", "train_step", "eval_step", "gather_eval_results", "GraphDataset", "NeighborLoader", "GNNConfig",
-           "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops", "partition"]
+           "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func", "ops", "partition", "optim"]

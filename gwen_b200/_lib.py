@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu", "optim.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
@@ -129,6 +129,7 @@ PROTOTYPES = {
     "gwen_gather_rows_bytes": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "gwen_mesh_mask_detect": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "gwen_rows_self_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
+    "gwen_adam_step": (_int, [_i32, _p, _p, _p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
 }
 
 _lib = None

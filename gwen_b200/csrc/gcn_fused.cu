@@ -71,6 +71,7 @@ struct FusedArgs {
   int prefetch;             // L2 prefetch distance of the source boxes, in items (0 = off)
   int epi_groups;           // epilogue warp groups (of 4 warps) that work: 2, or 1 when the A blocks fill the SM
   int epi_bufs;             // 2 KB staging buffers per epilogue warp: 2 = one TMA store in flight while the next packs
+  uint32_t wait_ns;         // poll interval of the stencil / epilogue warps on their barriers (0 = spin)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
@@ -250,9 +251,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       for (int k = 0; k < 4; ++k)
         pb2[k] = g.pre_bias ? pk2(__ldg(g.pre_bias + kb * BK + l * 8 + 2 * k), __ldg(g.pre_bias + kb * BK + l * 8 + 2 * k + 1))
                             : 0ull;
-      mbar_wait(smem_u32(&src_full[grp]), round & 1u);
+      mbar_wait_backoff(smem_u32(&src_full[grp]), round & 1u, g.wait_ns);
       // this A block fed item seq - nbuf: wait until the MMAs of its last N tile have retired
-      if (use > 0) mbar_wait(smem_u32(&a_empty[abuf * kbs + kb]), (use - 1u) & 1u);
+      if (use > 0) mbar_wait_backoff(smem_u32(&a_empty[abuf * kbs + kb]), (use - 1u) & 1u, g.wait_ns);
       const uint32_t a_blk = a_base + abuf * a_buf_bytes + uint32_t(kb) * kABlock;
       uint64_t s0[4], s1[4], s2[4];
       float dmid_prev = 0.0f;
@@ -310,7 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
         for (int nt = 0; nt < n_tiles; ++nt, ++seq_n) {
           const int n0 = nt * g.bn;
           const uint32_t acc = seq_n & 1u;
-          mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq_n >> 1) & 1u);
+          mbar_wait_backoff(smem_u32(&tmem_full_bar[acc]), (seq_n >> 1) & 1u, g.wait_ns);
           tc_fence_after();
           const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
           for (int sc = g2; sc < n_sub; sc += g.epi_groups) {
@@ -441,7 +442,7 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   if (rc != GWEN_OK) return rc;
   FusedArgs g{bias, dis_padded, dis_pitch, static_cast<int>(batch), static_cast<int>(h), static_cast<int>(w),
               k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x,
-              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs};
+              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs, wait_backoff_ns()};
   static const int prefetch_env = [] {
     const char* v = getenv("GWEN_FUSED_PREFETCH");
     // measured at the cfg 3 shapes (round 2, distance 0 / 1 / 2): 512->1024 8.65 / 9.62 / 9.70 ms, 512->256

@@ -48,6 +48,7 @@ struct Tc3Args {
   int batch;  // independent [m, k] x-slices / [m, n] y-slices (third TMA coordinate), same W
   int b_mn;  // B operand is MN-major: w is [reduction][n] row-major (dgrad: dx = dy W)
   int epi_cols;  // output columns per epilogue chunk and TMA store: 32 (64-byte rows) or 64 (128-byte rows)
+  uint32_t wait_ns;  // poll interval of the epilogue warps waiting for an accumulator (0 = spin)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
@@ -191,7 +192,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
         const int m0 = int(mb % mb_per_batch) * (2 * BM) + int(rank) * BM;
         const int n0 = nt * g.bn;
         const uint32_t acc = seq & 1u;
-        mbar_wait(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u);
+        mbar_wait_backoff(smem_u32(&tmem_full_bar[acc]), (seq >> 1) & 1u, g.wait_ns);
         tc_fence_after();
         const uint32_t t_addr = tmem_d + acc * uint32_t(g.bn) + (uint32_t(q * 32) << 16);
         if (g.epi_cols == 64) {
@@ -318,10 +319,14 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   if (rc != GWEN_OK) return rc;
   const int k_blocks = static_cast<int>(ceil_div(k, BK));
   const size_t stage_bytes = size_t(BM + bn / 2) * BK * 2;
-  static const int bufs = [] {
+  // staging buffers per epilogue warp: two (one TMA store in flight while the next chunk packs) for the shallow,
+  // store-bound reductions -- measured at M = 896 292 (round 2, 1 / 2 buffers): 64->1024 0.359 / 0.326 ms (cuBLAS
+  // 0.310), 1024->64 0.390 / 0.357, but 256->512 0.283 / 0.309 and 1024->512 0.801 / 0.812 (ring depth matters more)
+  static const int bufs_env = [] {
     const char* v = getenv("GWEN_TC3_BUFS");
-    return v && atoi(v) == 2 ? 2 : 1;
+    return v ? atoi(v) : 0;
   }();
+  const int bufs = (bufs_env == 1 || bufs_env == 2) ? bufs_env : ((k <= 128 || n_out <= 64) ? 2 : 1);
   // deep reductions are MMA-bound and want ring depth (6 stages need the room of 8 staging buffers);
   // shallow ones are store-bound and want all 16 epilogue warps
   static const int groups_env = [] {
@@ -359,7 +364,7 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   }();
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
-  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn, epi_cols};
+  Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn, epi_cols, wait_backoff_ns()};
   GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);

@@ -50,6 +50,7 @@ struct StencilArgs {
   uint32_t* flag_down_remote;
   uint32_t* ctl;              // local control words, see gwen_halo_peers
   uint64_t spin_timeout_ns;   // bound on every wait of the protocol (a sticky error word is set instead of hanging)
+  uint32_t wait_ns;           // poll interval of the consumer warps on the full barrier (0 = spin)
 };
 
 // control words of the peer-halo protocol (ctl[] in local device memory, zero-initialised)
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(576, 1)
       bv[k] = (a.bias && on) ? pk2(__ldg(a.bias + col + 2 * k), __ldg(a.bias + col + 2 * k + 1)) : 0ull;
     T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
     const bool relu = a.relu != 0;
-    mbar_wait(smem_u32(&full_bar[st]), round & 1u);
+    mbar_wait_backoff(smem_u32(&full_bar[st]), round & 1u, a.wait_ns);
     if (on) {
       for (int u = warp * RPW + sub; u < units; u += ncw * RPW) {
         const int r = u / nseg, cb = (u - r * nseg) * SEG;
@@ -456,6 +457,7 @@ static int stencil_fwd(const void* x, void* out, const float* dis_padded, int64_
     static const int timeout_ms = env_int2("GWEN_PEER_TIMEOUT_MS", 10000, 1, 3600000);
     a.spin_timeout_ns = uint64_t(timeout_ms) * 1000000ull;
   }
+  a.wait_ns = wait_backoff_ns();
   if (dis_pitch < int64_t(tiles_x - 1) * tw + dis_box_w)
     return set_err(GWEN_E_BADARG, "bordered dis pitch %lld < %lld needed for tile width %d",
                    (long long)dis_pitch, (long long)(int64_t(tiles_x - 1) * tw + dis_box_w), tw);

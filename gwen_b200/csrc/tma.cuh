@@ -83,6 +83,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Wait of a whole warp (or many warps) on a barrier that completes microseconds later: back off with nanosleep
+// between polls so the pollers leave the issue slots (and the power budget) to the warps that work.  ns = 0: spin.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  while (!done) {
+    if (ns) __nanosleep(ns);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+inline uint32_t wait_backoff_ns() {   // GWEN_WAIT_NS: poll interval of the bulk waiters (default 0 = spin)
+  static const uint32_t v = [] {
+    const char* e = getenv("GWEN_WAIT_NS");
+    const int x = e ? atoi(e) : 0;
+    return static_cast<uint32_t>(x < 0 ? 0 : (x > 100000 ? 100000 : x));
+  }();
+  return v;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }

@@ -402,6 +402,16 @@ int gwen_rows_self_fwd(const void* x, void* out, const int32_t* idx, int64_t n_i
                        int64_t feat, int64_t ldx, int64_t x_bstride, int64_t ldo, int64_t o_bstride,
                        int dtype, const float* bias, int epilogue, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step of the reference training loop (configs_train_gnn.optimizer.step(), src/gwen/models_gnn.py:373,
+ * with torch.optim.Adam(model.parameters(), lr = config["lr"] * 10), src/gwen/train_gnn.py:111): torch.optim.Adam's
+ * update (amsgrad = False) for `count` fp32 tensors in one launch per 32 tensors.
+ *   params / grads / exp_avg / exp_avg_sq : HOST arrays of `count` DEVICE pointers (fp32, numel[i] elements each)
+ *   step : 1-based step count of this update (bias corrections 1 - beta^step are formed on the host in fp64) */
+int gwen_adam_step(int32_t count, void* const* params, const void* const* grads, void* const* exp_avg,
+                   void* const* exp_avg_sq, const int64_t* numel, int64_t step, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

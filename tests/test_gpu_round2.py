@@ -365,3 +365,57 @@ def test_model_pair_fusion_is_bitwise_equal(dev, monkeypatch):
         assert gnn.pair_fusable(g, torch.empty(2, n, hid, device=dev, dtype=torch.bfloat16), d.conv2, d.conv3)
     assert not gnn.pair_fusable(g, torch.empty(2, n, hid, device=dev, dtype=torch.bfloat16), d.conv2, d.conv3)
     gw.clear_graph_cache()
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer step of the reference loop (models_gnn.py:373, torch.optim.Adam from train_gnn.py:111)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_adam_matches_torch_optim_adam(dev, wd):
+    torch.manual_seed(11)
+    shapes = [(1024, 64), (1024,), (512, 1024), (512,), (7, 3), (1,), (2049,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    frozen_a, frozen_b = torch.nn.Parameter(torch.ones(5, device=dev)), torch.nn.Parameter(torch.ones(5, device=dev))
+    oa = gw.optim.Adam(pa + [frozen_a], lr=1e-4, weight_decay=wd)          # the reference: lr = config["lr"] * 10 = 1e-4
+    ob = torch.optim.Adam(pb + [frozen_b], lr=1e-4, weight_decay=wd)
+    for step in range(6):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(a) * (10.0 ** (step - 3))
+            a.grad, b.grad = g.clone(), g.clone()
+        if step == 3:                       # a parameter without a gradient this step is skipped, like torch
+            pa[4].grad = pb[4].grad = None
+        oa.step()
+        ob.step()
+        for a, b in zip(pa, pb):
+            assert nmax(a, b) <= 2e-6
+    assert torch.equal(frozen_a, frozen_b) and not oa.state[frozen_a]
+    for a, b in zip(pa, pb):
+        assert nmax(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"]) <= 2e-6
+        assert nmax(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"]) <= 2e-6
+    with pytest.raises(NotImplementedError):
+        p16 = torch.nn.Parameter(torch.zeros(4, device=dev, dtype=torch.bfloat16))
+        p16.grad = torch.zeros_like(p16)
+        gw.optim.Adam([p16]).step()
+
+
+def test_train_step_with_fused_adam_matches_torch_adam(dev):
+    """gwen_b200.train_step (reference inner loop, models_gnn.py:364-375) with gwen_b200.optim.Adam against the same
+    loop with torch.optim.Adam: identical losses and parameters over three steps (fp32)."""
+    h, w, c, hid = 10, 12, 16, 64
+    n = h * w
+    ei = gw.grid(h, w, dev)
+    torch.manual_seed(5)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    ma, mb = gw.GNNModel(cfg).to(dev), gw.GNNModel(cfg).to(dev)
+    mb.load_state_dict(ma.state_dict())
+    oa, ob = gw.optim.Adam(ma.parameters(), lr=1e-3), torch.optim.Adam(mb.parameters(), lr=1e-3)
+    x = wts.features((n, c), 9).to(dev)
+    mask = (torch.arange(n, device=dev) % 5) == 4
+    for _ in range(3):
+        la = gw.train_step(ma, x, ei, mask, oa)
+        lb = gw.train_step(mb, x, ei, mask, ob)
+        assert abs(la.item() - lb.item()) <= 1e-6 * abs(lb.item())
+    for (na, a), (_, b) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert nmax(a, b) <= 1e-5, na
+    gw.clear_graph_cache()
