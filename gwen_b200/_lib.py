@@ -129,7 +129,7 @@ PROTOTYPES = {
     "gwen_gather_rows_bytes": (_int, [_p, _p, _p, _i64, _i64, _i64, _p]),
     "gwen_mesh_mask_detect": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p]),
     "gwen_rows_self_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
-    "gwen_adam_step": (_int, [_i32, _p, _p, _p, _p, _p, _i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _p]),
+    "gwen_adam_step": (_int, [_i32, _p, _p, _p, _p, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _p]),
 }
 
 _lib = None

@@ -26,7 +26,8 @@ struct AdamTable {
 constexpr int64_t kAdamChunk = int64_t(kAdamThreads) * 8;   // elements per block
 
 __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ AdamTable t, float step_size,
-                                                       float b1, float b2, float inv_bc2_sqrt, float eps, float wd) {
+                                                       float omb1, float b2, float omb2, float inv_bc2_sqrt,
+                                                       float eps, float wd) {
   // which tensor does this block belong to? (at most 32 entries: linear search)
   int ti = 0;
   while (ti + 1 < t.count && int64_t(blockIdx.x) >= t.blk0[ti + 1]) ++ti;
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ A
     float gi = g[i];
     const float pi = p[i];
     if (wd != 0.0f) gi = fmaf(wd, pi, gi);
-    const float mi = fmaf(gi - m[i], 1.0f - b1, m[i]);
-    const float vi = fmaf(1.0f - b2, gi * gi, b2 * v[i]);
+    const float mi = fmaf(gi - m[i], omb1, m[i]);          // lerp_(g, 1 - b1)
+    const float vi = fmaf(omb2, gi * gi, b2 * v[i]);      // mul_(b2).addcmul_(g, g, value = 1 - b2)
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
@@ -58,13 +59,14 @@ __global__ void __launch_bounds__(kAdamThreads) k_adam(const __grid_constant__ A
 using namespace gwen;
 
 extern "C" int gwen_adam_step(int32_t count, void* const* params, const void* const* grads, void* const* exp_avg,
-                              void* const* exp_avg_sq, const int64_t* numel, int64_t step, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, void* stream) {
+                              void* const* exp_avg_sq, const int64_t* numel, int64_t step, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, void* stream) {
   GWEN_CHECK_ARG(count >= 0 && step >= 1, "count must be >= 0 and step >= 1");
   if (count == 0) return GWEN_OK;
   GWEN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel, "null table");
-  const double bc1 = 1.0 - pow(double(beta1), double(step));
-  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  // hyper-parameters arrive as doubles (Python floats): 1 - beta and beta^step are formed in fp64 like torch does
+  const double bc1 = 1.0 - pow(beta1, double(step));
+  const double bc2 = 1.0 - pow(beta2, double(step));
   const float step_size = static_cast<float>(double(lr) / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   for (int32_t first = 0; first < count; first += kAdamMaxTensors) {
@@ -87,7 +89,8 @@ extern "C" int gwen_adam_step(int32_t count, void* const* params, const void* co
     if (blocks == 0) continue;
     GWEN_CHECK_ARG(blocks < INT32_MAX, "too many elements for one launch");
     k_adam<<<static_cast<unsigned>(blocks), kAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        t, step_size, beta1, beta2, inv_bc2_sqrt, eps, weight_decay);
+        t, step_size, static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+        inv_bc2_sqrt, static_cast<float>(eps), static_cast<float>(weight_decay));
     GWEN_LAUNCH_CHECK("k_adam");
   }
   return GWEN_OK;

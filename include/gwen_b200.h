@@ -409,8 +409,8 @@ int gwen_rows_self_fwd(const void* x, void* out, const int32_t* idx, int64_t n_i
  *   params / grads / exp_avg / exp_avg_sq : HOST arrays of `count` DEVICE pointers (fp32, numel[i] elements each)
  *   step : 1-based step count of this update (bias corrections 1 - beta^step are formed on the host in fp64) */
 int gwen_adam_step(int32_t count, void* const* params, const void* const* grads, void* const* exp_avg,
-                   void* const* exp_avg_sq, const int64_t* numel, int64_t step, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, void* stream);
+                   void* const* exp_avg_sq, const int64_t* numel, int64_t step, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, void* stream);
 
 #ifdef __cplusplus
 }
