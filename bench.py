@@ -264,7 +264,11 @@ def probe_full_forward_cfg3(dev):
     x_cpu = torch.randn(b, n, c, generator=xg)
     x = x_cpu.to(dev).to(torch.bfloat16)
     with torch.no_grad():
-        ms = _timed(lambda: model(x, ei), 2, 5)
+        _timed(lambda: model(x, ei), 2, 1)
+        fs = ClockSampler(dev.index or 0)          # SM clock / power WHILE the forward runs (it sits on the power cap)
+        t0 = time.time()
+        ms = _timed(lambda: model(x, ei), 1, 12)
+        fwd_clocks = fs.stop(t0, time.time())
         y = model(x, ei)
     e1 = gw.grid_edge_count(h, wd)
     flops = 2.0 * b * n * 1441792
@@ -273,6 +277,7 @@ def probe_full_forward_cfg3(dev):
                     "8 ensemble members per step, synthetic data, random-init weights" % e1,
         "ms_per_step": ms, "grid_steps_per_s": 1e3 / ms, "member_steps_per_s": b * 1e3 / ms,
         "edges_per_s": b * e1 * 6 / (ms * 1e-3), "flops_per_step": flops, "tflops": flops / (ms * 1e-3) / 1e12,
+        "clocks_during_forward": fwd_clocks,
         "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": flops / (ms * 1e-3) / 1e12 / tf_peak,
                      "note": "whole forward; lower bounds: %.1f ms (flops at the sustained bf16 peak), 14.9 ms "

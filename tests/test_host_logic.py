@@ -114,5 +114,6 @@ def test_fused_choice_threshold():
     X2 = type("X2", (), {"dtype": torch.bfloat16, "is_cuda": True, "shape": (1, 582 * 390, 64),
                          "numel": lambda self: 582 * 390 * 64})
     assert ops.gcn_fused_supported(G2, X2(), w) and not ops.gcn_fused_preferred(G2, X2(), w)   # small mesh
-    assert not ops.gcn_fused_supported(G, X(), torch.empty(1024, 512))                          # k_in = 512
+    assert ops.gcn_fused_supported(G, X(), torch.empty(1024, 512))                              # k_in = 512: one A buffer (round 2)
+    assert not ops.gcn_fused_supported(G, X(), torch.empty(1024, 576))                          # k_in > 512
     assert not ops.gcn_fused_supported(G, X(), torch.empty(64, 1024))
