@@ -750,6 +750,26 @@ def run_ours(args):
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = total_msgs * args.e2e_steps / (ms_e.item() * 1e-3)
     t_wall1 = time.time()
+    # where every rank's pinned buffers sit: (NUMA node of its GPU's PCIe root, CPUs of that node / CPUs allowed)
+    from gwen_b200.host_stream import gpu_numa_cpus
+    numa = gpu_numa_cpus(local_rank)
+    numa_info = {"rank": rank, "gpu_numa_node": None if numa is None else numa[0],
+                 "node_cpus": None if numa is None else len(numa[1]),
+                 "allowed_cpus": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+                 "e2e_ms_per_step": None}
+    e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0_.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1_.record()
+    torch.cuda.synchronize()
+    numa_info["e2e_ms_per_step"] = e0_.elapsed_time(e1_) / args.e2e_steps      # this rank's own time (not the max)
+    if world > 1:
+        all_numa = [None] * world
+        dist.all_gather_object(all_numa, numa_info)
+    else:
+        all_numa = [numa_info]
     del host_prop
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
@@ -795,7 +815,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
                     "d2h_bytes_per_step": out_host.numel() * 4 * world, "steps": args.e2e_steps,
                     "gbs_per_direction_per_gpu": x_host.numel() * 4 * args.e2e_steps / (ms_e.item() * 1e-3) / 1e9,
-                    "result_equals_device_path": e2e_ok, "api": e2e_api},
+                    "result_equals_device_path": e2e_ok, "api": e2e_api, "per_rank": all_numa,
+                    "numa_binding": "off (GWEN_NO_NUMA)" if os.environ.get("GWEN_NO_NUMA") else "pinned buffers first-touched on the GPU's NUMA node"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"kernel": "k_grid_stencil<float,16>", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,

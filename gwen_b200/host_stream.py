@@ -109,7 +109,7 @@ def pinned_near_gpu(shape, dtype, device_index: int) -> torch.Tensor:
     node), then the previous affinity is restored.  Without sysfs NUMA information this is a plain
     ``pin_memory()``."""
     import os
-    info = gpu_numa_cpus(device_index)
+    info = None if os.environ.get("GWEN_NO_NUMA") else gpu_numa_cpus(device_index)
     old = None
     if info is not None and hasattr(os, "sched_setaffinity"):
         try:

@@ -18,7 +18,7 @@ from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
 __all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred",
            "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
-           "rows_gather", "rows_scatter_", "dtype_code"]
+           "rows_gather", "rows_scatter_", "dtype_code", "clear_cast_cache"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
 
@@ -58,7 +58,14 @@ def _bias32(bias: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 # Parameter casts (fp32 master weights -> bf16 operand, any bias -> fp32) are cached per parameter
 # VERSION: the cast kernel runs once after each optimizer update instead of once per layer call
 # (forward, dgrad and the recompute paths all ask for the same cast).  The cache holds weak references.
+# The key is autograd's version counter: every in-place torch op (torch.optim included) and
+# gwen_b200.optim.Adam bump it; code that writes a parameter behind autograd's back (``p.data.copy_``, raw
+# pointers) must call ``torch.autograd.graph.increment_version(p)`` or ``ops.clear_cast_cache()``.
 _CAST_CACHE: dict = {}
+
+
+def clear_cast_cache() -> None:
+    _CAST_CACHE.clear()
 
 
 def _cast_cached(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

@@ -65,4 +65,9 @@ class Adam(torch.optim.Optimizer):
                         (C.c_int64 * n)(*[p.numel() for p in plist]), step, float(group["lr"]), float(b1), float(b2),
                         float(group["eps"]), float(group["weight_decay"]),
                         torch.cuda.current_stream().cuda_stream), "gwen_adam_step")
+                # the kernel wrote the parameters (and moments) through raw pointers: tell autograd, so that saved
+                # tensors are invalidated and version-keyed caches (ops._cast_cached: the bf16 copy of an fp32
+                # master weight) see the update
+                torch.autograd.graph.increment_version(
+                    plist + [self.state[p]["exp_avg"] for p in plist] + [self.state[p]["exp_avg_sq"] for p in plist])
         return loss

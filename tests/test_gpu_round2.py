@@ -419,3 +419,29 @@ def test_train_step_with_fused_adam_matches_torch_adam(dev):
     for (na, a), (_, b) in zip(ma.named_parameters(), mb.named_parameters()):
         assert nmax(a, b) <= 1e-5, na
     gw.clear_graph_cache()
+
+
+def test_mixed_precision_training_sees_fused_adam_updates(dev):
+    """bf16 activations with fp32 master weights (BASELINE config 5's numerics): the bf16 copy of a weight is cached per
+    parameter version, so an optimizer that writes parameters through raw pointers must bump the version --
+    gwen_b200.optim.Adam does; the model output follows the update exactly like with torch.optim.Adam."""
+    h, w, c, hid = 12, 16, 64, 128
+    n = h * w
+    ei = gw.grid(h, w, dev)
+    torch.manual_seed(7)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    ma, mb = gw.GNNModel(cfg).to(dev), gw.GNNModel(cfg).to(dev)
+    mb.load_state_dict(ma.state_dict())
+    oa, ob = gw.optim.Adam(ma.parameters(), lr=1e-2), torch.optim.Adam(mb.parameters(), lr=1e-2)
+    x = wts.features((n, c), 3).to(dev).bfloat16()
+    mask = (torch.arange(n, device=dev) % 3) == 0
+    with torch.no_grad():
+        y0 = ma(x, ei).clone()
+    for _ in range(2):
+        gw.train_step(ma, x, ei, mask, oa)
+        gw.train_step(mb, x, ei, mask, ob)
+    with torch.no_grad():
+        ya, yb = ma(x, ei), mb(x, ei)
+    assert not torch.equal(ya, y0)                          # the cached bf16 weights were refreshed
+    assert nmax(ya.float(), yb.float()) <= 2e-2             # same trajectory as torch.optim.Adam (bf16 activations)
+    gw.clear_graph_cache()
