@@ -58,6 +58,7 @@ constexpr uint32_t kSrcBox = (TH + 2) * kSrcRow;                 // 23040 B
 constexpr uint32_t kDisRow = 80u;                                // 18 floats padded to 20
 constexpr uint32_t kSrcStage = 24576u;                           // box + 10 dis rows, 1 KB aligned
 constexpr uint32_t kABlock = BM * 128u;                          // 128 rows x 64 bf16
+constexpr uint32_t kRingBlocks = 4;                              // A block ring of the one-N-tile mode (power of two)
 
 struct FusedArgs {
   const float* bias;
@@ -72,6 +73,10 @@ struct FusedArgs {
   int epi_groups;           // epilogue warp groups (of 4 warps) that work: 2, or 1 when the A blocks fill the SM
   int epi_bufs;             // 2 KB staging buffers per epilogue warp: 2 = one TMA store in flight while the next packs
   uint32_t wait_ns;         // poll interval of the stencil / epilogue warps on their barriers (0 = spin)
+  int ring;                 // 1: ONE N tile (n_out == bn), so an A block is read by exactly one K step: the A region is a
+                            // ring of kRingBlocks blocks (global block b -> slot b % 4, stencil group b & 1) instead of
+                            // a resident tile, and the shared memory it frees holds two source boxes per stencil group
+  int sg;                   // source stages per stencil group (1 or 2)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
@@ -86,7 +91,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     k_gcn_fused(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                 const __grid_constant__ CUtensorMap ymap, FusedArgs g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t src_full[2], src_empty[2], a_full[kMaxKb], a_empty[kMaxKb],
+  __shared__ __align__(8) uint64_t src_full[4], src_empty[4], a_full[kMaxKb], a_empty[kMaxKb],
       b_full[kMaxSB], b_empty[kMaxSB], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -96,11 +101,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   // shared-memory carve-up
   const uint32_t a_base = base;                                            // nbuf buffers x k_blocks x 16 KB
   const uint32_t a_buf_bytes = uint32_t(g.k_blocks) * kABlock;
-  const uint32_t src_base = a_base + uint32_t(g.nbuf) * a_buf_bytes;       // 2 x 24 KB
+  const uint32_t src_base = a_base + (g.ring ? kRingBlocks * kABlock : uint32_t(g.nbuf) * a_buf_bytes);  // 2 sg x 24 KB
+  const uint32_t SG = uint32_t(g.sg);
   const uint32_t nbuf = uint32_t(g.nbuf);
   const int kbs = g.k_blocks;                                              // barrier index = abuf * kbs + kb
   const uint32_t b_bytes = uint32_t(g.bn / 2) * 128u;
-  const uint32_t b_base = src_base + 2u * kSrcStage;                       // sb x b_bytes
+  const uint32_t b_base = src_base + 2u * SG * kSrcStage;                  // sb x b_bytes
   const uint32_t epi_base = b_base + uint32_t(g.sb) * b_bytes;             // 8 warps x 2 KB
   float* bias_s = reinterpret_cast<float*>(smem_raw + (epi_base - smem_u32(smem_raw)) +
                                            uint32_t(4 * g.epi_groups * g.epi_bufs) * 2048u);
@@ -124,9 +130,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     tma_prefetch_desc(&xmap);
     tma_prefetch_desc(&wmap);
     tma_prefetch_desc(&ymap);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 * g.sg; ++i) {
       mbar_init(smem_u32(&src_full[i]), 1);
-      mbar_init(smem_u32(&src_empty[i]), 4);           // the 4 warps of stencil group i
+      mbar_init(smem_u32(&src_empty[i]), 4);           // the 4 warps of the stencil group that owns the stage
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[i]), 2u * 4u * uint32_t(n_sub < g.epi_groups ? n_sub : g.epi_groups));
     }
@@ -154,10 +162,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ===== source producer: slab ring of 2 stages =====
-      // K block kb always goes through stage kb & 1 to stencil group kb & 1: a group then sees EVERY
-      // phase of the a_empty[kb] barriers it waits on (a parity wait must never skip a phase)
-      uint32_t uses[2] = {0u, 0u};
+    if (lane == 0) {  // ===== source producer =====
+      // Block (seq, kb) goes to stencil group kb & 1 (ring mode: global block index & 1), whose private ring has SG
+      // stages: a group then sees EVERY phase of the barriers it waits on (a parity wait must never skip a phase).
+      uint32_t cnt[2] = {0u, 0u};
       for (int64_t seq = 0; seq < my_items; ++seq) {
         int b, r0, c0;
         item_of(seq, b, r0, c0);
@@ -170,7 +178,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
                          : "memory");
         }
         for (int kb = 0; kb < g.k_blocks; ++kb) {
-          const uint32_t s = uint32_t(kb) & 1u, round = uses[s]++;
+          const uint32_t grp = g.ring ? uint32_t(seq * g.k_blocks + kb) & 1u : uint32_t(kb) & 1u;
+          const uint32_t jj = cnt[grp]++;
+          const uint32_t s = grp * SG + jj % SG, round = jj / SG;
           if (round > 0) mbar_wait(smem_u32(&src_empty[s]), (round - 1) & 1u);
           const uint32_t bar = smem_u32(&src_full[s]);
           const uint32_t dst = src_base + s * kSrcStage;
@@ -195,18 +205,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
           tc_fence_after();
           const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
           for (int kb = 0; kb < g.k_blocks; ++kb, ++it_b) {
-            if (nt == 0) mbar_wait(smem_u32(&a_full[abuf * kbs + kb]), aphase);
+            // A block of (seq, kb): resident slot abuf * kbs + kb, or (ring mode) slot blk % ra of the block ring
+            const uint32_t blk = uint32_t(seq) * uint32_t(g.k_blocks) + uint32_t(kb);
+            const uint32_t aslot = g.ring ? blk % kRingBlocks : abuf * uint32_t(kbs) + uint32_t(kb);
+            const uint32_t afull_phase = g.ring ? (blk / kRingBlocks) & 1u : aphase;
+            if (nt == 0) mbar_wait(smem_u32(&a_full[aslot]), afull_phase);
             const uint32_t s = it_b % uint32_t(g.sb);
             mbar_wait(smem_u32(&b_full[s]), (it_b / uint32_t(g.sb)) & 1u);
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc(a_base + abuf * a_buf_bytes + uint32_t(kb) * kABlock);
+            const uint64_t adesc = make_smem_desc(a_base + aslot * kABlock);
             const uint64_t bdesc = make_smem_desc(b_base + s * b_bytes);
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; ++kk)
               umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc,
                             (kb | kk) ? 1u : 0u);
             umma_commit_pair(smem_u32(&b_empty[s]));
-            if (nt == n_tiles - 1) umma_commit_pair(smem_u32(&a_empty[abuf * kbs + kb]));  // block is free
+            if (nt == n_tiles - 1) umma_commit_pair(smem_u32(&a_empty[aslot]));  // block is free
           }
           umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
         }
@@ -233,28 +247,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     const int sub = lane >> 3, l = lane & 7;               // 4 sub-warps of 8 lanes (64 features)
     const int su = wg * 4 + sub;                           // 0..15: (tile row, half row)
     const int tr = su >> 1, cb = (su & 1) * SEG;
-    const uint32_t xs = src_base + uint32_t(grp) * kSrcStage;
-    const uint32_t ds = xs + kSrcBox;
-    const uint32_t x0 = xs + uint32_t(tr) * kSrcRow + uint32_t(cb) * 128u + uint32_t(l) * 16u;
-    const uint32_t x1 = x0 + kSrcRow, x2 = x1 + kSrcRow;
-    const uint32_t q0 = ds + uint32_t(tr) * kDisRow + uint32_t(cb) * 4u;
-    const uint32_t q1 = q0 + kDisRow, q2 = q1 + kDisRow;
     const int row0 = tr * FT_W + cb;                       // first A row of this unit
     const bool pre_relu = g.pre_relu != 0;
-    uint32_t round = 0;
+    uint32_t jj = 0;                                       // blocks this group has aggregated so far
     for (int64_t seq = 0; seq < my_items; ++seq)
-    for (int kb = grp; kb < g.k_blocks; kb += 2, ++round) {
-      const uint32_t abuf = uint32_t(seq % nbuf), use = uint32_t(seq / nbuf);
+    for (int kb = 0; kb < g.k_blocks; ++kb) {
+      const uint32_t blk = uint32_t(seq) * uint32_t(g.k_blocks) + uint32_t(kb);
+      if ((g.ring ? blk & 1u : uint32_t(kb) & 1u) != uint32_t(grp)) continue;   // the other group's block
+      const uint32_t sstage = uint32_t(grp) * SG + jj % SG, sphase = (jj / SG) & 1u;
+      ++jj;
+      const uint32_t xs = src_base + sstage * kSrcStage;
+      const uint32_t ds = xs + kSrcBox;
+      const uint32_t x0 = xs + uint32_t(tr) * kSrcRow + uint32_t(cb) * 128u + uint32_t(l) * 16u;
+      const uint32_t x1 = x0 + kSrcRow, x2 = x1 + kSrcRow;
+      const uint32_t q0 = ds + uint32_t(tr) * kDisRow + uint32_t(cb) * 4u;
+      const uint32_t q1 = q0 + kDisRow, q2 = q1 + kDisRow;
+      const uint32_t abuf = uint32_t(seq % nbuf);
+      // A block slot and how often it has been used before (ring mode: global block ring)
+      const uint32_t aslot = g.ring ? blk % kRingBlocks : abuf * uint32_t(kbs) + uint32_t(kb);
+      const uint32_t use = g.ring ? blk / kRingBlocks : uint32_t(seq / nbuf);
       // per-feature bias of the aggregated row (the previous layer's epilogue moved into this producer)
       uint64_t pb2[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         pb2[k] = g.pre_bias ? pk2(__ldg(g.pre_bias + kb * BK + l * 8 + 2 * k), __ldg(g.pre_bias + kb * BK + l * 8 + 2 * k + 1))
                             : 0ull;
-      mbar_wait_backoff(smem_u32(&src_full[grp]), round & 1u, g.wait_ns);
-      // this A block fed item seq - nbuf: wait until the MMAs of its last N tile have retired
-      if (use > 0) mbar_wait_backoff(smem_u32(&a_empty[abuf * kbs + kb]), (use - 1u) & 1u, g.wait_ns);
-      const uint32_t a_blk = a_base + abuf * a_buf_bytes + uint32_t(kb) * kABlock;
+      mbar_wait_backoff(smem_u32(&src_full[sstage]), sphase, g.wait_ns);
+      // this A block was used before: wait until the MMAs of its last N tile have retired
+      if (use > 0) mbar_wait_backoff(smem_u32(&a_empty[aslot]), (use - 1u) & 1u, g.wait_ns);
+      const uint32_t a_blk = a_base + aslot * kABlock;
       uint64_t s0[4], s1[4], s2[4];
       float dmid_prev = 0.0f;
 #pragma unroll
@@ -289,8 +310,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(smem_u32(&src_empty[grp]));
-        mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[abuf * kbs + kb]), 0));
+        mbar_arrive(smem_u32(&src_empty[sstage]));
+        mbar_arrive_cluster(mapa_u32(smem_u32(&a_full[aslot]), 0));
       }
     }
   } else {
@@ -390,27 +411,38 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   GWEN_CHECK_ARG(dis_rows >= int64_t(tiles_y) * TH + 2, "bordered dis has too few rows");
   // two A buffers while they fit in 8 blocks (k_in <= 256), else one
   const int nbuf = 2 * k_blocks <= kMaxKb ? 2 : 1;
-  // N tile: 256 columns unless the resident A blocks leave no room for two 16 KB W stages
-  // one working epilogue group (4 staging buffers) when a single A buffer already fills the SM
-  const int epi_groups = nbuf == 2 ? 2 : 1;
   // double-buffered epilogue staging when the A blocks leave room (k_in <= 128: the store-bound layers, 64 -> 1024)
   static const int ebufs_env = [] {
     const char* v = getenv("GWEN_FUSED_EPI_BUFS");
     return v ? atoi(v) : 0;
   }();
   const int epi_bufs = (ebufs_env == 1 || ebufs_env == 2) ? ebufs_env : (k_blocks <= 2 ? 2 : 1);
-  const size_t fixed = size_t(nbuf) * size_t(k_blocks) * kABlock + 2 * kSrcStage + size_t(4 * epi_groups * epi_bufs) * 2048 +
-                       align_up(size_t(n_out) * 4, 1024) + 1024;
+  static const int ring_env = [] {   // GWEN_FUSED_RING=0: never use the A ring (A/B tests)
+    const char* v = getenv("GWEN_FUSED_RING");
+    return v ? atoi(v) : 1;
+  }();
   const size_t cap = 226 * 1024;
-  // N tile: the one that keeps more W bytes in flight (the W ring is what is left of shared memory), 256 on a tie
-  int bn = 0;
-  size_t best = 0;
+  // Configuration: N tile bn in {256, 128}; ring mode when the layer has ONE N tile (n_out == bn: an A block is read by
+  // a single K step, so 4 ring blocks replace the resident tile); two source stages per stencil group when they fit
+  // next to at least two W stages.  Among the candidates: the one that keeps more W bytes in flight, 256 on a tie.
+  int bn = 0, ring = 0, sg = 1, epi_groups = 2;
+  size_t best = 0, fixed = 0;
   for (int c : {256, 128}) {
     if (n_out % c) continue;
     const size_t bb = size_t(c / 2) * 128;
-    if (fixed + 2 * bb > cap) continue;
-    const size_t fl = std::min<size_t>(kMaxSB, (cap - fixed) / bb) * bb;
-    if (fl > best) { best = fl; bn = c; }
+    const int ring_c = (ring_env && n_out == c && k_blocks >= 2) ? 1 : 0;
+    // one working epilogue group (4 staging buffers) when a single resident A buffer already fills the SM
+    const int eg = (ring_c || nbuf == 2) ? 2 : 1;
+    const size_t a_bytes = ring_c ? size_t(kRingBlocks) * kABlock : size_t(nbuf) * size_t(k_blocks) * kABlock;
+    for (int sgc : {2, 1}) {
+      const size_t fx = a_bytes + size_t(2 * sgc) * kSrcStage + size_t(4 * eg * epi_bufs) * 2048 +
+                        align_up(size_t(n_out) * 4, 1024) + 1024;
+      if (fx + 2 * bb > cap) continue;
+      const size_t fl = std::min<size_t>(kMaxSB, (cap - fx) / bb) * bb;
+      if (sgc == 2 && fl < 3 * bb && fl < 32768) continue;      // the second source stage must not starve the W ring
+      if (fl > best) { best = fl; bn = c; ring = ring_c; sg = sgc; epi_groups = eg; fixed = fx; }
+      break;                                                     // the deepest source ring that fits for this bn
+    }
   }
   if (!bn) return set_err(GWEN_E_NOSUPPORT, "fused layer does not fit in shared memory");
   const size_t b_bytes = size_t(bn / 2) * 128;
@@ -442,7 +474,7 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   if (rc != GWEN_OK) return rc;
   FusedArgs g{bias, dis_padded, dis_pitch, static_cast<int>(batch), static_cast<int>(h), static_cast<int>(w),
               k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x,
-              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs, wait_backoff_ns()};
+              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs, wait_backoff_ns(), ring, sg};
   static const int prefetch_env = [] {
     const char* v = getenv("GWEN_FUSED_PREFETCH");
     // measured at the cfg 3 shapes (round 2, distance 0 / 1 / 2): 512->1024 8.65 / 9.62 / 9.70 ms, 512->256
