@@ -77,6 +77,8 @@ struct FusedArgs {
                             // ring of kRingBlocks blocks (global block b -> slot b % 4, stencil group b & 1) instead of
                             // a resident tile, and the shared memory it frees holds two source boxes per stencil group
   int sg;                   // source stages per stencil group (1 or 2)
+  int kouter;               // ring mode with TWO N tiles whose accumulators are both resident (2 bn = 512 TMEM columns):
+                            // K block outer, N tile inner, so an A block is read by two consecutive K steps and freed
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1,
@@ -197,6 +199,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     if (leader && lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc = make_idesc_pair(g.bn);
       uint32_t it_b = 0, seq_n = 0;
+      if (g.kouter) {
+        // both accumulators (N tiles 0 and 1) stay resident for the whole item; accumulator nt is tile nt
+        for (int64_t seq = 0; seq < my_items; ++seq) {
+          for (int kb = 0; kb < g.k_blocks; ++kb) {
+            const uint32_t blk = uint32_t(seq) * uint32_t(g.k_blocks) + uint32_t(kb);
+            const uint32_t aslot = blk % kRingBlocks;
+            mbar_wait(smem_u32(&a_full[aslot]), (blk / kRingBlocks) & 1u);
+            const uint64_t adesc = make_smem_desc(a_base + aslot * kABlock);
+            for (int nt = 0; nt < 2; ++nt, ++it_b) {
+              // the epilogue must have drained this accumulator of the previous item before its first MMA
+              if (kb == 0 && seq > 0) mbar_wait(smem_u32(&tmem_empty_bar[nt]), uint32_t(seq - 1) & 1u);
+              const uint32_t s = it_b % uint32_t(g.sb);
+              mbar_wait(smem_u32(&b_full[s]), (it_b / uint32_t(g.sb)) & 1u);
+              tc_fence_after();
+              const uint64_t bdesc = make_smem_desc(b_base + s * b_bytes);
+              const uint32_t d_addr = tmem_d + uint32_t(nt) * uint32_t(g.bn);
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk)
+                umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+              umma_commit_pair(smem_u32(&b_empty[s]));
+            }
+            umma_commit_pair(smem_u32(&a_empty[aslot]));       // both N tiles have read the block
+          }
+          umma_commit_pair(smem_u32(&tmem_full_bar[0]));
+          umma_commit_pair(smem_u32(&tmem_full_bar[1]));
+        }
+      } else
       for (int64_t seq = 0; seq < my_items; ++seq) {
         const uint32_t abuf = uint32_t(seq % nbuf), aphase = uint32_t(seq / nbuf) & 1u;
         for (int nt = 0; nt < n_tiles; ++nt, ++seq_n) {
@@ -229,10 +258,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   } else if (warp == 2) {
     if (lane == 0) {  // ===== W producer (both CTAs) =====
       uint32_t it_b = 0;
+      const int outer = g.kouter ? g.k_blocks : n_tiles, inner = g.kouter ? n_tiles : g.k_blocks;
       for (int64_t seq = 0; seq < my_items; ++seq) {
-        for (int nt = 0; nt < n_tiles; ++nt) {
-          const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
-          for (int kb = 0; kb < g.k_blocks; ++kb, ++it_b) {
+        for (int o = 0; o < outer; ++o) {
+          for (int i = 0; i < inner; ++i, ++it_b) {     // the order in which the MMA issuer consumes the W tiles
+            const int nt = g.kouter ? i : o, kb = g.kouter ? o : i;
+            const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
             const uint32_t s = it_b % uint32_t(g.sb), round = it_b / uint32_t(g.sb);
             if (round > 0) mbar_wait(smem_u32(&b_empty[s]), (round - 1) & 1u);
             if (leader) mbar_expect_tx(smem_u32(&b_full[s]), 2 * b_bytes);
@@ -417,30 +448,39 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
     return v ? atoi(v) : 0;
   }();
   const int epi_bufs = (ebufs_env == 1 || ebufs_env == 2) ? ebufs_env : (k_blocks <= 2 ? 2 : 1);
-  static const int ring_env = [] {   // GWEN_FUSED_RING=0: never use the A ring (A/B tests)
+  static const int ring_env = [] {   // GWEN_FUSED_RING=0: never use the A ring; 1: one-N-tile layers only (A/B tests)
     const char* v = getenv("GWEN_FUSED_RING");
-    return v ? atoi(v) : 1;
+    return v ? atoi(v) : 2;
   }();
   const size_t cap = 226 * 1024;
   // Configuration: N tile bn in {256, 128}; ring mode when the layer has ONE N tile (n_out == bn: an A block is read by
   // a single K step, so 4 ring blocks replace the resident tile); two source stages per stencil group when they fit
   // next to at least two W stages.  Among the candidates: the one that keeps more W bytes in flight, 256 on a tie.
-  int bn = 0, ring = 0, sg = 1, epi_groups = 2;
+  static const int sg_env = [] {     // GWEN_FUSED_SG=1|2: force the source stages per stencil group (sweeps)
+    const char* v = getenv("GWEN_FUSED_SG");
+    return v ? atoi(v) : 0;
+  }();
+  int bn = 0, ring = 0, sg = 1, epi_groups = 2, kouter = 0;
   size_t best = 0, fixed = 0;
   for (int c : {256, 128}) {
     if (n_out % c) continue;
     const size_t bb = size_t(c / 2) * 128;
-    const int ring_c = (ring_env && n_out == c && k_blocks >= 2) ? 1 : 0;
+    // two N tiles whose accumulators fill tensor memory exactly (n_out = 512): K block outer, ring mode as well
+    // (measured at the cfg 3 mesh, B = 8: 256->512 3.42 -> 2.84 ms; 128->512 1.89 -> 2.00, hence k_in >= 256)
+    const int kouter_c = (ring_env >= 2 && n_out == 2 * c && 2 * c == 512 && k_blocks >= 4) ? 1 : 0;
+    const int ring_c = ((ring_env && n_out == c && k_blocks >= 2) || kouter_c) ? 1 : 0;
     // one working epilogue group (4 staging buffers) when a single resident A buffer already fills the SM
     const int eg = (ring_c || nbuf == 2) ? 2 : 1;
     const size_t a_bytes = ring_c ? size_t(kRingBlocks) * kABlock : size_t(nbuf) * size_t(k_blocks) * kABlock;
     for (int sgc : {2, 1}) {
+      if (sg_env && sgc != sg_env) continue;
+      if (kouter_c && sgc == 2 && !sg_env) continue;   // K-outer: the W ring (two tiles per K block) needs the room
       const size_t fx = a_bytes + size_t(2 * sgc) * kSrcStage + size_t(4 * eg * epi_bufs) * 2048 +
                         align_up(size_t(n_out) * 4, 1024) + 1024;
       if (fx + 2 * bb > cap) continue;
       const size_t fl = std::min<size_t>(kMaxSB, (cap - fx) / bb) * bb;
       if (sgc == 2 && fl < 3 * bb && fl < 32768) continue;      // the second source stage must not starve the W ring
-      if (fl > best) { best = fl; bn = c; ring = ring_c; sg = sgc; epi_groups = eg; fixed = fx; }
+      if (fl > best) { best = fl; bn = c; ring = ring_c; sg = sgc; epi_groups = eg; fixed = fx; kouter = kouter_c; }
       break;                                                     // the deepest source ring that fits for this bn
     }
   }
@@ -474,7 +514,7 @@ extern "C" int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, co
   if (rc != GWEN_OK) return rc;
   FusedArgs g{bias, dis_padded, dis_pitch, static_cast<int>(batch), static_cast<int>(h), static_cast<int>(w),
               k_blocks, static_cast<int>(n_out), bn, sb, (epilogue & GWEN_EPI_RELU) ? 1 : 0, tiles_y, pairs_x,
-              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs, wait_backoff_ns(), ring, sg};
+              nbuf, pre_bias, (pre_epilogue & GWEN_EPI_RELU) ? 1 : 0, 0, epi_groups, epi_bufs, wait_backoff_ns(), ring, sg, kouter};
   static const int prefetch_env = [] {
     const char* v = getenv("GWEN_FUSED_PREFETCH");
     // measured at the cfg 3 shapes (round 2, distance 0 / 1 / 2): 512->1024 8.65 / 9.62 / 9.70 ms, 512->256

@@ -204,6 +204,8 @@ def _rows_view(t: torch.Tensor):
 # 1158 x 774 meshes: -4 % .. -11 % vs the two-kernel path; on 582 x 390 it is slower).
 FUSED_MIN_ITEMS = 3500
 FUSED_MAX_K = 512       # widest input the fused kernel keeps resident (one A buffer above 256)
+import os as _os
+FUSED_MIN_K = int(_os.environ.get("GWEN_FUSED_MIN_K", "64"))   # narrowest input that takes the fused kernel
 
 
 def gcn_fused_supported(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
@@ -212,7 +214,7 @@ def gcn_fused_supported(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) 
     import os
     k, n = weight.shape[1], weight.shape[0]
     return (os.environ.get("GWEN_NO_FUSED") is None and graph.is_plain_mesh and x.dtype == torch.bfloat16
-            and x.is_cuda and 64 <= k <= FUSED_MAX_K and k % 64 == 0 and n % 128 == 0 and n <= 8192)
+            and x.is_cuda and max(64, FUSED_MIN_K) <= k <= FUSED_MAX_K and k % 64 == 0 and n % 128 == 0 and n <= 8192)
 
 
 def gcn_fused_preferred(graph: GraphCSR, x: torch.Tensor, weight: torch.Tensor) -> bool:
