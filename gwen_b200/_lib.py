@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu", "optim.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_b2b.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu", "optim.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
@@ -101,6 +101,8 @@ PROTOTYPES = {
     "gwen_grid_stencil_peer_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
                                           _int, _p, _int, _i32, _i32, C.POINTER(HaloPeersStruct), _p]),
     "gwen_gcn_fused_fwd": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _int, _p]),
+    "gwen_linear_b2b_supported": (_int, [_i64, _i64, _i64, _i64, _int]),
+    "gwen_linear_b2b_fwd": (_int, [_p, _p, _p, _int, _p, _p, _int, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p]),
     "gwen_linear_fwd_workspace_bytes": (_int, [_i64, _i64, _i64, _int, C.POINTER(_sz)]),
     "gwen_linear_fwd_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _sz, _p]),

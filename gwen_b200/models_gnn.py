@@ -18,7 +18,8 @@ import torch
 from torch import nn
 
 from .graph import GraphCSR, get_graph
-from .nn import GCNConv, gcn_conv_pair, pair_fusable
+from . import ops
+from .nn import GCNConv, b2b_fusable, gcn_conv_b2b_project, gcn_conv_pair, pair_fusable
 
 __all__ = ["GNNConfig", "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func"]
 
@@ -45,13 +46,26 @@ class DownConvLayers(nn.Module):
         self.conv5 = GCNConv(h // 8, h // 16)
 
     def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
-        x = self.conv1(x, edge_index, relu=True)
         if x.is_cuda and x.dtype == torch.bfloat16:
-            # inference on a large mesh: conv2's aggregation + bias + ReLU run inside conv3's fused kernel
-            # (gwen_b200.nn.gcn_conv_pair, bitwise equal to the two separate layers)
+            # inference on a large mesh (both bitwise equal to the layers run one by one):
+            #  * conv1 and conv2's projection back to back in one kernel (gwen_b200.nn.gcn_conv_b2b_project): conv1's
+            #    1024-wide output never reaches HBM;
+            #  * conv2's aggregation + bias + ReLU inside conv3's fused kernel (gwen_b200.nn.gcn_conv_pair)
             graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))
-            if pair_fusable(graph, x, self.conv2, self.conv3):
-                return gcn_conv_pair(x, graph, self.conv2, self.conv3, relu_b=True)
+            p2 = None
+            if b2b_fusable(x, self.conv1, self.conv2):
+                p2 = gcn_conv_b2b_project(x, graph, self.conv1, self.conv2)
+                x2_like = p2
+            else:
+                x = self.conv1(x, edge_index, relu=True)
+                x2_like = x
+            if pair_fusable(graph, x2_like, self.conv2, self.conv3):
+                return gcn_conv_pair(x if p2 is None else None, graph, self.conv2, self.conv3, relu_b=True, p=p2)
+            if p2 is not None:
+                x = ops.aggregate(graph, p2, self.conv2.bias, True)
+                return self.conv3(x, edge_index, relu=True)
+        else:
+            x = self.conv1(x, edge_index, relu=True)
         x = self.conv2(x, edge_index, relu=True)
         x = self.conv3(x, edge_index, relu=True)
         return x
@@ -69,6 +83,12 @@ class UpConvLayers(nn.Module):
 
     def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
         x = self.upconv3(x, edge_index, relu=True)
+        if x.is_cuda and x.dtype == torch.bfloat16 and b2b_fusable(x, self.upconv4, self.upconv5):
+            # inference on a large mesh: upconv4 and upconv5's projection back to back, upconv4's 1024-wide output
+            # never reaches HBM (bitwise equal to the two layers)
+            graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))
+            p5 = gcn_conv_b2b_project(x, graph, self.upconv4, self.upconv5)
+            return ops.aggregate(graph, p5, self.upconv5.bias, False)
         x = self.upconv4(x, edge_index, relu=True)
         x = self.upconv5(x, edge_index)
         return x

@@ -22,7 +22,7 @@ from torch import Tensor
 from . import ops
 from .graph import GraphCSR, get_graph
 
-__all__ = ["GCNConv", "gcn_conv", "gcn_conv_pair", "pair_fusable"]
+__all__ = ["GCNConv", "gcn_conv", "gcn_conv_pair", "pair_fusable", "b2b_fusable", "gcn_conv_b2b_project"]
 
 
 class _GCNConvFn(torch.autograd.Function):
@@ -105,13 +105,47 @@ def pair_fusable(graph: GraphCSR, x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv
 
 
 @torch.no_grad()
-def gcn_conv_pair(x: Tensor, graph: GraphCSR, conv_a: "GCNConv", conv_b: "GCNConv", relu_b: bool) -> Tensor:
-    """``epi_b(conv_b(relu(conv_a(x))))`` with conv_a's aggregation fused into conv_b's kernel (inference)."""
-    p = ops.linear(x, conv_a.lin.weight)
+def gcn_conv_pair(x: Optional[Tensor], graph: GraphCSR, conv_a: "GCNConv", conv_b: "GCNConv", relu_b: bool,
+                  p: Optional[Tensor] = None) -> Tensor:
+    """``epi_b(conv_b(relu(conv_a(x))))`` with conv_a's aggregation fused into conv_b's kernel (inference).
+    ``p``: conv_a's un-aggregated projection ``x Wa^T`` when the caller already has it (gcn_conv_b2b_project)."""
+    if p is None:
+        p = ops.linear(x, conv_a.lin.weight)
     b_last = conv_b.in_channels >= conv_b.out_channels
     q = ops.gcn_fused(graph, p, conv_b.lin.weight, None if b_last else conv_b.bias, False if b_last else relu_b,
                       pre_bias=conv_a.bias, pre_relu=True)
     return ops.aggregate(graph, q, conv_b.bias, relu_b) if b_last else q
+
+
+# Back-to-back projections (inference): conv_a aggregates FIRST (in < out) and conv_b projects FIRST (in > out):
+#     conv_b(relu(conv_a(x))) = A_hat ( relu((A_hat x) Wa^T + ba) Wb^T ) + bb
+# The hidden tensor relu(...) -- the widest of the stack (GWEN: conv1 -> conv2 and upconv4 -> upconv5, 1024 wide) --
+# is produced and consumed inside ONE kernel (gwen_linear_b2b_fwd) and never reaches HBM:
+#     a = A_hat x                           (mesh stencil / CSR kernel at conv_a's narrow input width)
+#     p = relu(a Wa^T + ba) Wb^T            (two tcgen05 products back to back)
+# and p, conv_b's un-aggregated projection, goes on to conv_b's aggregation (or into the pair fusion above).
+# The hidden block is rounded to bf16 exactly where the layer-by-layer path stores conv_a's output.
+B2B_FUSION = _os.environ.get("GWEN_B2B_FUSION", "1") != "0"
+B2B_MIN_ROWS = 500_000     # rows (members x nodes) from which the one kernel beats the two layers' kernels (measured)
+
+
+def b2b_fusable(x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv") -> bool:
+    if not B2B_FUSION or torch.is_grad_enabled() and (x.requires_grad or conv_a.lin.weight.requires_grad
+                                                      or conv_b.lin.weight.requires_grad):
+        return False
+    if conv_a.in_channels >= conv_a.out_channels or conv_b.in_channels <= conv_b.out_channels or \
+            conv_b.in_channels != conv_a.out_channels:
+        return False
+    if x.numel() // max(1, x.shape[-1]) < B2B_MIN_ROWS:
+        return False
+    return ops.linear_b2b_supported(x, conv_a.lin.weight, conv_b.lin.weight)
+
+
+@torch.no_grad()
+def gcn_conv_b2b_project(x: Tensor, graph: GraphCSR, conv_a: "GCNConv", conv_b: "GCNConv") -> Tensor:
+    """``relu(conv_a(x)) Wb^T``: conv_a with its ReLU, then conv_b's projection, the hidden tensor kept on chip."""
+    a = ops.aggregate(graph, x)
+    return ops.linear_b2b(a, conv_a.lin.weight, conv_a.bias, True, conv_b.lin.weight)
 
 
 class _Linear(torch.nn.Module):

@@ -17,7 +17,7 @@ from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
 __all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred",
-           "linear", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
+           "linear", "linear_b2b", "linear_b2b_supported", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
            "rows_gather", "rows_scatter_", "dtype_code", "clear_cast_cache"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
@@ -307,6 +307,47 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
                                        code, _ptr(bias32), _lib.EPI_RELU if relu else 0, _ptr(ws), need.value,
                                        _stream()), "gwen_linear_fwd")
     return y.reshape(tuple(x.shape[:-1]) + (n_out,))
+
+
+def linear_b2b_supported(x: torch.Tensor, weight1: torch.Tensor, weight2: torch.Tensor) -> bool:
+    """True when ``linear_b2b`` can serve this pair of projections (bf16, k1 in {64, .., 512}, n1 % 256 == 0,
+    n2 % 64 == 0 and n2 <= 256 or n2 % 256 == 0, at least 256 rows; GWEN_NO_B2B unset)."""
+    import os
+    if os.environ.get("GWEN_NO_B2B") is not None or not x.is_cuda or x.dtype != torch.bfloat16:
+        return False
+    m = x.numel() // max(1, x.shape[-1])
+    return bool(lib().gwen_linear_b2b_supported(m, weight1.shape[1], weight1.shape[0], weight2.shape[0],
+                                                dtype_code(x.dtype)))
+
+
+def linear_b2b(x: torch.Tensor, weight1: torch.Tensor, bias1: Optional[torch.Tensor], relu1: bool,
+               weight2: torch.Tensor, bias2: Optional[torch.Tensor] = None, relu2: bool = False,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = epi2(epi1(x @ weight1.T + bias1) @ weight2.T + bias2) in one kernel (gwen_linear_b2b_fwd): the hidden
+    tensor ``epi1(...)`` ([..., N1]) never reaches HBM.  x [..., K1] bf16, weight1 [N1, K1], weight2 [N2, N1]."""
+    _require_cuda(x, "x")
+    _require_cuda(weight1, "weight1")
+    _require_cuda(weight2, "weight2")
+    k1 = x.shape[-1]
+    n1, n2 = weight1.shape[0], weight2.shape[0]
+    if weight1.shape[1] != k1 or weight2.shape[1] != n1:
+        raise ValueError("weights are %s and %s, x has %d features" % (tuple(weight1.shape), tuple(weight2.shape), k1))
+    w1 = _cast_cached(weight1, x.dtype)
+    w2 = _cast_cached(weight2, x.dtype)
+    b1, b2 = _bias32(bias1), _bias32(bias2)
+    x2 = x.reshape(-1, k1)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    m = x2.shape[0]
+    with torch.cuda.device(x2.device):
+        if out is None:
+            out = torch.empty(tuple(x.shape[:-1]) + (n2,), dtype=x.dtype, device=x.device)
+        if not out.is_contiguous() or out.dtype != x.dtype or out.numel() != m * n2:
+            raise ValueError("out must be a contiguous [..., N2] tensor of x's dtype")
+        check(lib().gwen_linear_b2b_fwd(_ptr(x2), _ptr(w1), _ptr(b1), _lib.EPI_RELU if relu1 else 0, _ptr(w2), _ptr(b2),
+                                        _lib.EPI_RELU if relu2 else 0, _ptr(out), m, k1, n1, n2, k1, n2,
+                                        dtype_code(x.dtype), _stream()), "gwen_linear_b2b_fwd")
+    return out
 
 
 def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -260,6 +260,22 @@ int gwen_gcn_fused_fwd(const void* x, const void* weight, void* y, const float* 
                        int pre_epilogue, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Two projections back to back (bf16): y = epi2( epi1(x W1^T + bias1) W2^T + bias2 ) in ONE kernel.
+ * Where a GCNConv that projects last (in < out: conv1, upconv4; models_gnn.py:147,204) is followed by one
+ * that projects first (in > out: conv2, upconv5; torch_geometric GCNConv.forward `x = self.lin(x)`), the wide
+ * hidden tensor between them never reaches HBM: per 256-column chunk the first product's accumulator is turned
+ * into bf16 (rounded exactly as gwen_linear_fwd stores it) in shared memory and consumed as the A operand of
+ * the second product.  Results equal gwen_linear_fwd(epi1) followed by gwen_linear_fwd(epi2).
+ *   x : bf16 [m, k1] (row pitch ldx)   w1 : bf16 [n1, k1]   w2 : bf16 [n2, n1]   y : bf16 [m, n2] (pitch ldy)
+ *   bias1 fp32 [n1] / bias2 fp32 [n2] nullable; epilogue1 / epilogue2: GWEN_EPI_RELU or 0
+ *   k1 in {64, .., 512}, n1 % 256 == 0, n2 % 64 == 0 and (n2 <= 256 or n2 % 256 == 0), m >= 256:
+ *   gwen_linear_b2b_supported returns 1, else 0 (then gwen_linear_b2b_fwd returns GWEN_E_NOSUPPORT). */
+int gwen_linear_b2b_supported(int64_t m, int64_t k1, int64_t n1, int64_t n2, int dtype);
+int gwen_linear_b2b_fwd(const void* x, const void* w1, const float* bias1, int epilogue1, const void* w2,
+                        const float* bias2, int epilogue2, void* y, int64_t m, int64_t k1, int64_t n1,
+                        int64_t n2, int64_t ldx, int64_t ldy, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2  dense projection.  Replaces Linear(bias=False) inside GCNConv (F.linear -> cuBLAS,
  * SURVEY.md table 2.3 row 6) and, through the epilogue, the bias add and ReLU when the
  * projection runs after the aggregation:

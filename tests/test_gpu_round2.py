@@ -368,6 +368,78 @@ def test_model_pair_fusion_is_bitwise_equal(dev, monkeypatch):
 
 
 # ---------------------------------------------------------------------------------------------
+# two projections back to back (gwen_linear_b2b_fwd): conv1 -> conv2's projection, upconv4 -> upconv5's projection
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [256, 1000, 4096 + 77, 256 * 151 + 3])        # ragged row blocks, > 1 item per CTA pair
+@pytest.mark.parametrize("k1,n1,n2", [(64, 1024, 512), (512, 1024, 64), (64, 256, 64), (128, 256, 128),
+                                      (256, 768, 256), (320, 512, 192)])
+def test_linear_b2b_matches_two_projections(dev, m, k1, n1, n2):
+    """y = relu(x W1^T + b1) W2^T + b2 in one kernel: bitwise equal to two gwen_linear_fwd launches (the hidden block
+    is rounded to bf16 exactly where the first launch stores it), and within the bf16 bar of the fp32 product."""
+    torch.manual_seed(m + k1 + n2)
+    x = torch.randn(m, k1, device=dev).bfloat16()
+    w1 = (torch.randn(n1, k1, device=dev) / k1 ** 0.5).bfloat16()
+    w2 = (torch.randn(n2, n1, device=dev) / n1 ** 0.5).bfloat16()
+    b1 = torch.randn(n1, device=dev) * 0.1
+    b2 = torch.randn(n2, device=dev) * 0.1
+    assert ops.linear_b2b_supported(x, w1, w2)
+    guard = torch.full((m + 64, n2), 7.0, device=dev, dtype=torch.bfloat16)      # red zone behind the output rows
+    y = ops.linear_b2b(x, w1, b1, True, w2, b2, False, out=guard[:m])
+    hid = ops.linear(x, w1, b1, relu=True)
+    y2 = ops.linear(hid, w2, b2)
+    assert torch.equal(y, y2)
+    assert bool((guard[m:] == 7.0).all())
+    ref = torch.relu(x.double() @ w1.double().t() + b1.double()).bfloat16().double() @ w2.double().t() + b2.double()
+    assert nmax(y, ref) <= 1e-2
+    # no bias, ReLU on the output
+    y = ops.linear_b2b(x, w1, None, False, w2, None, True)
+    assert torch.equal(y, ops.linear(ops.linear(x, w1), w2, relu=True))
+
+
+def test_linear_b2b_rejects_what_it_cannot_serve(dev):
+    x = torch.zeros(512, 96, device=dev, dtype=torch.bfloat16)
+    w1 = torch.zeros(256, 96, device=dev, dtype=torch.bfloat16)
+    w2 = torch.zeros(64, 256, device=dev, dtype=torch.bfloat16)
+    assert not ops.linear_b2b_supported(x, w1, w2)                               # k1 % 64
+    with pytest.raises(RuntimeError, match="back-to-back"):
+        ops.linear_b2b(x, w1, None, True, w2)
+    assert not ops.linear_b2b_supported(x.float(), w1.float(), w2.float())       # bf16 only
+
+
+def test_model_b2b_fusion_is_bitwise_equal(dev, monkeypatch):
+    """Under no_grad the model runs conv1 -> conv2 and upconv4 -> upconv5 through the back-to-back kernel: same bits
+    as the layer-by-layer path, with and without the conv2 -> conv3 pair fusion; not used when grad is enabled."""
+    from gwen_b200 import nn as gnn
+    h, w, c, hid = 24, 40, 64, 1024
+    n = h * w
+    torch.manual_seed(5)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    model = gw.GNNModel(cfg).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.normal_(0, 0.1)
+    ei = gw.grid(h, w, dev)
+    x = wts.features((2, n, c), 72).bfloat16().to(dev)
+    d, u = model.conv_layers.down_conv_layers, model.conv_layers.up_conv_layers
+    with torch.no_grad():
+        monkeypatch.setattr(gnn, "B2B_FUSION", False)
+        y_seq = model(x, ei)
+        monkeypatch.setattr(gnn, "B2B_FUSION", True)
+        monkeypatch.setattr(gnn, "B2B_MIN_ROWS", 0)
+        assert gnn.b2b_fusable(x, d.conv1, d.conv2)
+        assert gnn.b2b_fusable(torch.empty(2, n, hid // 2, device=dev, dtype=torch.bfloat16), u.upconv4, u.upconv5)
+        assert not gnn.b2b_fusable(x, d.conv2, d.conv3)
+        y_b2b = model(x, ei)
+        monkeypatch.setattr(ops, "FUSED_MIN_ITEMS", 0)                           # + pair fusion fed by the b2b output
+        y_both = model(x, ei)
+    assert torch.equal(y_b2b, y_seq)
+    assert torch.equal(y_both, y_seq)
+    assert not gnn.b2b_fusable(x, d.conv1, d.conv2)                              # grad enabled: layer by layer
+    gw.clear_graph_cache()
+
+
+# ---------------------------------------------------------------------------------------------
 # optimizer step of the reference loop (models_gnn.py:373, torch.optim.Adam from train_gnn.py:111)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("wd", [0.0, 0.01])
