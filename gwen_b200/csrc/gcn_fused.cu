@@ -182,7 +182,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
         for (int kb = 0; kb < g.k_blocks; ++kb) {
           const uint32_t grp = g.ring ? uint32_t(seq * g.k_blocks + kb) & 1u : uint32_t(kb) & 1u;
           const uint32_t jj = cnt[grp]++;
-          const uint32_t s = grp * SG + jj % SG, round = jj / SG;
+          const uint32_t s = grp * SG + (jj & (SG - 1u)), round = jj >> (SG - 1u);   // SG is 1 or 2
           if (round > 0) mbar_wait(smem_u32(&src_empty[s]), (round - 1) & 1u);
           const uint32_t bar = smem_u32(&src_full[s]);
           const uint32_t dst = src_base + s * kSrcStage;
@@ -198,7 +198,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
   } else if (warp == 1) {
     if (leader && lane == 0) {  // ===== MMA issuer =====
       const uint32_t idesc = make_idesc_pair(g.bn);
-      uint32_t it_b = 0, seq_n = 0;
+      // W ring stage / phase and the A buffer index are kept incrementally: a division by a run-time ring depth costs
+      // this single thread ~100 cycles per K block (measured in linear_b2b.cu: a third of the issuer's time)
+      uint32_t seq_n = 0, ws = 0, wph = 0;
+      const uint32_t sbn = uint32_t(g.sb);
       if (g.kouter) {
         // both accumulators (N tiles 0 and 1) stay resident for the whole item; accumulator nt is tile nt
         for (int64_t seq = 0; seq < my_items; ++seq) {
@@ -207,11 +210,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
             const uint32_t aslot = blk % kRingBlocks;
             mbar_wait(smem_u32(&a_full[aslot]), (blk / kRingBlocks) & 1u);
             const uint64_t adesc = make_smem_desc(a_base + aslot * kABlock);
-            for (int nt = 0; nt < 2; ++nt, ++it_b) {
+            for (int nt = 0; nt < 2; ++nt) {
               // the epilogue must have drained this accumulator of the previous item before its first MMA
               if (kb == 0 && seq > 0) mbar_wait(smem_u32(&tmem_empty_bar[nt]), uint32_t(seq - 1) & 1u);
-              const uint32_t s = it_b % uint32_t(g.sb);
-              mbar_wait(smem_u32(&b_full[s]), (it_b / uint32_t(g.sb)) & 1u);
+              const uint32_t s = ws;
+              mbar_wait(smem_u32(&b_full[s]), wph);
+              if (++ws == sbn) { ws = 0; wph ^= 1u; }
               tc_fence_after();
               const uint64_t bdesc = make_smem_desc(b_base + s * b_bytes);
               const uint32_t d_addr = tmem_d + uint32_t(nt) * uint32_t(g.bn);
@@ -227,20 +231,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
         }
       } else
       for (int64_t seq = 0; seq < my_items; ++seq) {
-        const uint32_t abuf = uint32_t(seq % nbuf), aphase = uint32_t(seq / nbuf) & 1u;
+        const uint32_t abuf = nbuf == 2 ? uint32_t(seq) & 1u : 0u;
+        const uint32_t aphase = (nbuf == 2 ? uint32_t(seq >> 1) : uint32_t(seq)) & 1u;
         for (int nt = 0; nt < n_tiles; ++nt, ++seq_n) {
           const uint32_t acc = seq_n & 1u, use = seq_n >> 1;
           if (use > 0) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use - 1) & 1u);
           tc_fence_after();
           const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
-          for (int kb = 0; kb < g.k_blocks; ++kb, ++it_b) {
+          for (int kb = 0; kb < g.k_blocks; ++kb) {
             // A block of (seq, kb): resident slot abuf * kbs + kb, or (ring mode) slot blk % ra of the block ring
             const uint32_t blk = uint32_t(seq) * uint32_t(g.k_blocks) + uint32_t(kb);
             const uint32_t aslot = g.ring ? blk % kRingBlocks : abuf * uint32_t(kbs) + uint32_t(kb);
             const uint32_t afull_phase = g.ring ? (blk / kRingBlocks) & 1u : aphase;
             if (nt == 0) mbar_wait(smem_u32(&a_full[aslot]), afull_phase);
-            const uint32_t s = it_b % uint32_t(g.sb);
-            mbar_wait(smem_u32(&b_full[s]), (it_b / uint32_t(g.sb)) & 1u);
+            const uint32_t s = ws;
+            mbar_wait(smem_u32(&b_full[s]), wph);
+            if (++ws == sbn) { ws = 0; wph ^= 1u; }
             tc_fence_after();
             const uint64_t adesc = make_smem_desc(a_base + aslot * kABlock);
             const uint64_t bdesc = make_smem_desc(b_base + s * b_bytes);
@@ -257,17 +263,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     }
   } else if (warp == 2) {
     if (lane == 0) {  // ===== W producer (both CTAs) =====
-      uint32_t it_b = 0;
+      uint32_t s = 0, ph = 0;
+      bool wrapped = false;
       const int outer = g.kouter ? g.k_blocks : n_tiles, inner = g.kouter ? n_tiles : g.k_blocks;
       for (int64_t seq = 0; seq < my_items; ++seq) {
         for (int o = 0; o < outer; ++o) {
-          for (int i = 0; i < inner; ++i, ++it_b) {     // the order in which the MMA issuer consumes the W tiles
+          for (int i = 0; i < inner; ++i) {     // the order in which the MMA issuer consumes the W tiles
             const int nt = g.kouter ? i : o, kb = g.kouter ? o : i;
             const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
-            const uint32_t s = it_b % uint32_t(g.sb), round = it_b / uint32_t(g.sb);
-            if (round > 0) mbar_wait(smem_u32(&b_empty[s]), (round - 1) & 1u);
+            if (wrapped) mbar_wait(smem_u32(&b_empty[s]), ph ^ 1u);
             if (leader) mbar_expect_tx(smem_u32(&b_full[s]), 2 * b_bytes);
             tma_load_3d_pair(b_base + s * b_bytes, &wmap, kb * BK, n0, 0, mapa_u32(smem_u32(&b_full[s]), 0));
+            if (++s == uint32_t(g.sb)) { s = 0; ph ^= 1u; wrapped = true; }
           }
         }
       }
@@ -285,7 +292,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
     for (int kb = 0; kb < g.k_blocks; ++kb) {
       const uint32_t blk = uint32_t(seq) * uint32_t(g.k_blocks) + uint32_t(kb);
       if ((g.ring ? blk & 1u : uint32_t(kb) & 1u) != uint32_t(grp)) continue;   // the other group's block
-      const uint32_t sstage = uint32_t(grp) * SG + jj % SG, sphase = (jj / SG) & 1u;
+      const uint32_t sstage = uint32_t(grp) * SG + (jj & (SG - 1u)), sphase = (jj >> (SG - 1u)) & 1u;   // SG is 1 or 2
       ++jj;
       const uint32_t xs = src_base + sstage * kSrcStage;
       const uint32_t ds = xs + kSrcBox;
@@ -293,10 +300,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
       const uint32_t x1 = x0 + kSrcRow, x2 = x1 + kSrcRow;
       const uint32_t q0 = ds + uint32_t(tr) * kDisRow + uint32_t(cb) * 4u;
       const uint32_t q1 = q0 + kDisRow, q2 = q1 + kDisRow;
-      const uint32_t abuf = uint32_t(seq % nbuf);
+      const uint32_t abuf = nbuf == 2 ? uint32_t(seq) & 1u : 0u;
       // A block slot and how often it has been used before (ring mode: global block ring)
       const uint32_t aslot = g.ring ? blk % kRingBlocks : abuf * uint32_t(kbs) + uint32_t(kb);
-      const uint32_t use = g.ring ? blk / kRingBlocks : uint32_t(seq / nbuf);
+      const uint32_t use = g.ring ? blk / kRingBlocks : (nbuf == 2 ? uint32_t(seq >> 1) : uint32_t(seq));
       // per-feature bias of the aggregated row (the previous layer's epilogue moved into this producer)
       uint64_t pb2[4];
 #pragma unroll

@@ -123,16 +123,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer (both CTAs) =====
-      uint32_t it = 0;
+      // stage index / phase kept incrementally: a division by the run-time ring depth costs this single thread ~100
+      // cycles per K block
+      uint32_t s = 0, ph = 0;
+      bool wrapped = false;
       for (int64_t idx = 0; idx < my_tiles; ++idx) {
         int mb, nt;
         tile_of(idx, mb, nt);
         const int bi = int(mb / mb_per_batch);
         const int m0 = int(mb % mb_per_batch) * (2 * BM) + int(rank) * BM;
         const int n0 = nt * g.bn + int(rank) * (g.bn / 2);
-        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-          const uint32_t s = it % uint32_t(g.stages), round = it / uint32_t(g.stages);
-          if (round > 0) mbar_wait(smem_u32(&empty_bar[s]), (round - 1) & 1u);
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          if (wrapped) mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
           if (leader) mbar_expect_tx(smem_u32(&full_bar[s]), 2 * stage_bytes);
           const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
           const uint32_t dst = base + s * stage_bytes;
@@ -143,21 +145,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
             for (int i = 0; i < g.bn / 128; ++i)
               tma_load_3d_pair(dst + a_bytes + uint32_t(i) * 8192u, &bmap, n0 + 64 * i, kb * BK, 0, bar);
           }
+          if (++s == uint32_t(g.stages)) { s = 0; ph ^= 1u; wrapped = true; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {  // ===== MMA issuer (leader CTA) =====
       const uint32_t idesc = make_idesc_pair(g.bn) | (g.b_mn ? (1u << 16) : 0u);  // bit 16: B MN-major
-      uint32_t it = 0, seq = 0;
+      uint32_t seq = 0, s = 0, ph = 0;
       for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
         const uint32_t acc = seq & 1u, use = seq >> 1;
         if (use > 0) mbar_wait(smem_u32(&tmem_empty_bar[acc]), (use - 1) & 1u);
         tc_fence_after();
         const uint32_t d_addr = tmem_d + acc * uint32_t(g.bn);
-        for (int kb = 0; kb < g.k_blocks; ++kb, ++it) {
-          const uint32_t s = it % uint32_t(g.stages);
-          mbar_wait(smem_u32(&full_bar[s]), (it / uint32_t(g.stages)) & 1u);
+        for (int kb = 0; kb < g.k_blocks; ++kb) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
           const uint32_t a_addr = base + s * stage_bytes;
           const uint64_t adesc = make_smem_desc(a_addr);
@@ -170,6 +172,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
             umma_f16_pair(d_addr, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk) * bstep, idesc,
                           (kb | kk) ? 1u : 0u);
           umma_commit_pair(smem_u32(&empty_bar[s]));
+          if (++s == uint32_t(g.stages)) { s = 0; ph ^= 1u; }
         }
         umma_commit_pair(smem_u32(&tmem_full_bar[acc]));
       }

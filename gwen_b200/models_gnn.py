@@ -53,7 +53,7 @@ class DownConvLayers(nn.Module):
             #  * conv2's aggregation + bias + ReLU inside conv3's fused kernel (gwen_b200.nn.gcn_conv_pair)
             graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))
             p2 = None
-            if b2b_fusable(x, self.conv1, self.conv2):
+            if b2b_fusable(x, self.conv1, self.conv2, "down"):
                 p2 = gcn_conv_b2b_project(x, graph, self.conv1, self.conv2)
                 x2_like = p2
             else:
@@ -83,7 +83,7 @@ class UpConvLayers(nn.Module):
 
     def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
         x = self.upconv3(x, edge_index, relu=True)
-        if x.is_cuda and x.dtype == torch.bfloat16 and b2b_fusable(x, self.upconv4, self.upconv5):
+        if x.is_cuda and x.dtype == torch.bfloat16 and b2b_fusable(x, self.upconv4, self.upconv5, "up"):
             # inference on a large mesh: upconv4 and upconv5's projection back to back, upconv4's 1024-wide output
             # never reaches HBM (bitwise equal to the two layers)
             graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))

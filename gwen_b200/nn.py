@@ -126,10 +126,13 @@ def gcn_conv_pair(x: Optional[Tensor], graph: GraphCSR, conv_a: "GCNConv", conv_
 # and p, conv_b's un-aggregated projection, goes on to conv_b's aggregation (or into the pair fusion above).
 # The hidden block is rounded to bf16 exactly where the layer-by-layer path stores conv_a's output.
 B2B_FUSION = _os.environ.get("GWEN_B2B_FUSION", "1") != "0"
+B2B_PAIRS = _os.environ.get("GWEN_B2B_PAIRS", "down,up").split(",")   # which pairs may fuse: conv1->conv2 (down), upconv4->upconv5 (up)
 B2B_MIN_ROWS = 500_000     # rows (members x nodes) from which the one kernel beats the two layers' kernels (measured)
 
 
-def b2b_fusable(x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv") -> bool:
+def b2b_fusable(x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv", which: Optional[str] = None) -> bool:
+    if which is not None and which not in B2B_PAIRS:
+        return False
     if not B2B_FUSION or torch.is_grad_enabled() and (x.requires_grad or conv_a.lin.weight.requires_grad
                                                       or conv_b.lin.weight.requires_grad):
         return False
