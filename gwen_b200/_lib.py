@@ -15,13 +15,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libgwen_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_b2b.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu", "optim.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "aggregate.cu", "stencil.cu", "linear.cu", "linear_tc.cu", "linear_tc3.cu", "linear_wgrad_tc.cu", "loss.cu", "gcn_fused.cu", "linear_b2b.cu", "linear_tf32x3.cu", "linear_wgrad_tf32x3.cu", "neighbor.cu", "mesh_mask.cu", "optim.cu", "locality.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "tcgen05.cuh", "stencil_common.cuh"]
 
 GWEN_F32, GWEN_BF16 = 0, 1
 GRAPH_ADD_SELF_LOOPS, GRAPH_IMPROVED, GRAPH_TRANSPOSE = 1, 2, 4
 EPI_NONE, EPI_RELU = 0, 1
 GWEN_E_NOSUPPORT = -5
+PLAN_GATHER = 1
 
 
 def nvcc_command(out_path: str = LIB_PATH) -> list:
@@ -91,6 +92,8 @@ PROTOTYPES = {
     "gwen_tile_plan_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "gwen_tile_plan_build": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p,
                                     _p, _p, _p, _sz, _p]),
+    "gwen_locality_workspace_bytes": (_int, [_i64, C.POINTER(_sz)]),
+    "gwen_locality_tiles": (_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "gwen_uniform_tiles": (_int, [_i64, _i32, _p, _p]),
     "gwen_grid_tiles": (_int, [_i64, _i64, _i32, _i32, _p, _p, _p]),
     "gwen_aggregate_tiled_fwd": (_int, [C.POINTER(TilePlanStruct), _p, _p, _i64, _i64, _i64,

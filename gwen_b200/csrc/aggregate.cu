@@ -298,6 +298,13 @@ struct TiledArgs {
   uint32_t rec_bytes;    // one metadata buffer: records, then messages
   uint32_t meta_bytes;
   int num_stages;
+  // gather mode (plans whose runs are single rows: locality tiles of an arbitrarily numbered graph):
+  // the producer warp copies row slabs with 16-byte cp.async instead of one TMA box per run
+  int gather;            // 0: TMA boxes per run; 1: 16-byte cp.async per row slab; 2: one bulk copy per row slab
+  int gather_warps;      // producer warps of gather mode 1
+  const void* x;
+  int64_t ldx, x_bstride;
+  uint32_t runs_off;     // offset of the tile's run list inside a metadata buffer (gather mode)
 };
 
 __device__ __forceinline__ int4 lds_i4(uint32_t saddr) {
@@ -322,6 +329,43 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
       : "memory");
 }
 
+__device__ __forceinline__ int lds_s32(uint32_t saddr) {
+  int r;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(saddr));
+  return r;
+}
+// 16 bytes global -> shared past L1 (LDGSTS.128); completion is collected by cp_async_mbar_arrive
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// the executing thread's arrival on `bar` happens when all of its earlier cp.async copies have landed;
+// .noinc: the arrival is one of the barrier's expected count
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Up to U messages of one destination row out of shared memory: message words (staged row, weight), then the
+// source slabs (LDS.128), then the fp32 accumulation in message order.
+template <typename T, int U>
+__device__ __forceinline__ void reduce_batch(float* acc, uint32_t mp, uint32_t stage, uint32_t slab_bytes, int n) {
+  constexpr int VN = Vec16<T>::N;
+  uint2 m[U];
+  uint4 v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < n) m[u] = lds_u2(mp + u * 8u);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < n) v[u] = lds_v4(stage + m[u].x * slab_bytes);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u < n) {
+      float f[VN];
+      Vec16<T>::unpack(v[u], f);
+      axpy_exact<T, VN>(acc, __uint_as_float(m[u].y), f);
+    }
+}
+
 // Persistent, warp-specialised CTA; work item = (tile, batch b, feature slab), tile-major.
 // Shared memory holds NS data stages and two metadata buffers (row records + messages of a tile).
 //   producer (last warp, one lane): for every item waits for its stage to be empty, then issues
@@ -344,11 +388,12 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
   const uint32_t stage0 = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t meta0 = stage0 + uint32_t(ns) * a.stage_bytes;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int ncw = nwarps - 1;  // consumer warps
+  const int npw = a.gather == 1 ? a.gather_warps : 1;  // producer warps
+  const int ncw = nwarps - npw;                         // consumer warps
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&xmap);
     for (int i = 0; i < ns; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&full_bar[i]), a.gather == 1 ? 32 * npw : 1);
       mbar_init(smem_u32(&empty_bar[i]), ncw);
     }
     for (int i = 0; i < 2; ++i) {
@@ -365,16 +410,99 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
                            ? (a.num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
   const int64_t n_items = int64_t(my_tiles) * per_tile;
 
+  if (warp >= ncw && a.gather) {
+    // ===== producers, gather mode: single source rows instead of TMA boxes =====
+    // Per tile the run list (one source row id per staged row) arrives with the records and messages (producer
+    // warp 0); per item the tile's row slabs are copied either
+    //   gather == 1: with 16-byte cp.async (LDGSTS), CPR lanes per row slab, rows dealt round-robin to the
+    //                producer warps; every lane arrives on full[stage] through cp.async.mbarrier.arrive.noinc
+    //                (the barrier expects 32 x producer warps arrivals), or
+    //   gather == 2: with one cp.async.bulk per row slab (UBLKCP), a row per lane, completing on full[stage]
+    //                by byte count (one producer warp).
+    const int pw = warp - ncw;
+    const int cpr = int(slab_bytes >> 4);          // 16-byte chunks per row slab: 8, 16 or 32
+    const int rpp = 32 / cpr;                      // rows per pass of one warp
+    const int lrow = lane / cpr, lchunk = lane % cpr;
+    const char* xbase = static_cast<const char*>(a.x);
+    const uint32_t pitch = uint32_t(a.ldx * int64_t(sizeof(T)));   // < 4 GB (checked by the launcher)
+    int st = 0;
+    uint32_t st_round = 0;
+    int seq = 0, rem = 0, b = 0, slab = 0, r0 = 0, r1 = 0;
+    for (int64_t it = 0; it < n_items; ++it) {
+      const int t = a.tile_begin + int(blockIdx.x) + seq * int(gridDim.x);
+      const int mb_i = seq & 1;
+      if (rem == 0) {
+        r0 = __ldg(a.run_ptr + t);
+        r1 = __ldg(a.run_ptr + t + 1);
+      }
+      const int r0a = r0 & ~3;
+      if (rem == 0) {  // first item of a tile: its records, messages and run list
+        if (pw == 0 && lane == 0) {
+          if (seq >= 2) mbar_wait(smem_u32(&mempty_bar[mb_i]), uint32_t((seq >> 1) - 1) & 1u);
+          const int p0 = __ldg(a.tile_ptr + t), p1 = __ldg(a.tile_ptr + t + 1);
+          const int m0 = __ldg(a.tmsg_base + t) & ~1, m1 = __ldg(a.tmsg_base + t + 1);
+          const uint32_t rb = uint32_t(p1 - p0) * 16u, mb = uint32_t((m1 - m0 + 1) & ~1) * 8u;
+          const uint32_t lb = uint32_t((r1 - r0a + 3) & ~3) * 4u;
+          const uint32_t bar = smem_u32(&mfull_bar[mb_i]);
+          const uint32_t dst = meta0 + uint32_t(mb_i) * a.meta_bytes;
+          mbar_expect_tx(bar, rb + mb + lb);
+          bulk_g2s(dst, a.trec + p0, rb, bar);
+          if (mb) bulk_g2s(dst + a.rec_bytes, a.tmsg + m0, mb, bar);
+          if (lb) bulk_g2s(dst + a.runs_off, a.run_start + r0a, lb, bar);
+        }
+        mbar_wait(smem_u32(&mfull_bar[mb_i]), uint32_t(seq >> 1) & 1u);
+      }
+      if (st_round > 0) mbar_wait(smem_u32(&empty_bar[st]), (st_round - 1) & 1u);
+      const uint32_t runs = meta0 + uint32_t(mb_i) * a.meta_bytes + a.runs_off + uint32_t(r0 - r0a) * 4u;
+      const uint32_t sbase = stage0 + uint32_t(st) * a.stage_bytes;
+      const int n_rows = r1 - r0;
+      const int64_t col0 = int64_t(slab) * a.slab_elems;
+      if (a.gather == 2) {
+        const int64_t left = (a.feat - col0) * int64_t(sizeof(T));
+        const uint32_t row_bytes = left < int64_t(slab_bytes) ? uint32_t(left) : slab_bytes;
+        const uint32_t bar = smem_u32(&full_bar[st]);
+        if (lane == 0) mbar_expect_tx(bar, uint32_t(n_rows) * row_bytes);
+        __syncwarp();
+        const char* xb = xbase + (int64_t(b) * a.x_bstride + col0) * int64_t(sizeof(T));
+        for (int i = lane; i < n_rows; i += 32) {
+          const uint32_t row = uint32_t(lds_s32(runs + uint32_t(i) * 4u));
+          bulk_g2s(sbase + uint32_t(i) * slab_bytes, xb + uint64_t(row) * pitch, row_bytes, bar);
+        }
+      } else {
+        const int64_t col = col0 + int64_t(lchunk) * VN;
+        const char* xb = xbase + (int64_t(b) * a.x_bstride + col) * int64_t(sizeof(T));
+        const uint32_t dst = sbase + uint32_t(lchunk) * 16u;
+        const int step = rpp * npw;
+        if (col < a.feat) {
+          constexpr int UN = 4;
+          int i0 = pw * rpp + lrow;
+          for (; i0 + (UN - 1) * step < n_rows; i0 += UN * step) {   // full groups: no per-copy predicate
+            uint32_t rows[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) rows[u] = uint32_t(lds_s32(runs + uint32_t(i0 + u * step) * 4u));
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+              cp_async16(dst + uint32_t(i0 + u * step) * slab_bytes, xb + uint64_t(rows[u]) * pitch);
+          }
+          for (; i0 < n_rows; i0 += step)
+            cp_async16(dst + uint32_t(i0) * slab_bytes, xb + uint64_t(uint32_t(lds_s32(runs + uint32_t(i0) * 4u))) * pitch);
+        }
+        cp_async_mbar_arrive(smem_u32(&full_bar[st]));
+      }
+      if (++st == ns) { st = 0; ++st_round; }
+      if (++slab == a.slabs) { slab = 0; ++b; }
+      if (++rem == per_tile) { rem = 0; b = 0; ++seq; }
+    }
+    return;
+  }
   if (warp == ncw) {
     // ===== producer =====
     if (lane == 0) {
       int st = 0;
       uint32_t st_round = 0;  // how many times the stage ring wrapped
+      int seq = 0, rem = 0, b = 0, slab = 0;
       for (int64_t it = 0; it < n_items; ++it) {
-        const int seq = int(it / per_tile);
         const int t = a.tile_begin + int(blockIdx.x) + seq * int(gridDim.x);
-        const int rem = int(it % per_tile);
-        const int b = rem / a.slabs, slab = rem % a.slabs;
         if (rem == 0) {  // first item of a tile: its records and messages
           const int mb_i = seq & 1;
           if (seq >= 2) mbar_wait(smem_u32(&mempty_bar[mb_i]), uint32_t((seq >> 1) - 1) & 1u);
@@ -396,6 +524,8 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
           tma_load_3d(dst + uint32_t(r - r0) * run_bytes, &xmap, slab * a.slab_elems,
                       __ldg(a.run_start + r), b, bar);
         if (++st == ns) { st = 0; ++st_round; }
+        if (++slab == a.slabs) { slab = 0; ++b; }
+        if (++rem == per_tile) { rem = 0; b = 0; ++seq; }
       }
     }
     return;
@@ -405,11 +535,9 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
   const int sub = lane / LPR, l = lane % LPR;
   int st = 0;
   uint32_t st_round = 0;
+  int seq = 0, rem = 0, b = 0, slab = 0, n_rows = 0;   // item = (tile seq, batch b, slab), kept incrementally
   for (int64_t it = 0; it < n_items; ++it) {
-    const int seq = int(it / per_tile);
     const int t = a.tile_begin + int(blockIdx.x) + seq * int(gridDim.x);
-    const int rem = int(it % per_tile);
-    const int b = rem / a.slabs, slab = rem % a.slabs;
     const int64_t f0 = int64_t(slab) * a.slab_elems;
     const int64_t col = f0 + int64_t(l) * VN;
     const bool on = col < a.feat;
@@ -418,7 +546,7 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
     const uint32_t msgs = recs + a.rec_bytes;
     if (rem == 0) mbar_wait(smem_u32(&mfull_bar[seq & 1]), uint32_t(seq >> 1) & 1u);
     mbar_wait(smem_u32(&full_bar[st]), st_round & 1u);
-    const int n_rows = __ldg(a.tile_ptr + t + 1) - __ldg(a.tile_ptr + t);
+    if (rem == 0) n_rows = __ldg(a.tile_ptr + t + 1) - __ldg(a.tile_ptr + t);
     T* ob = static_cast<T*>(a.out) + b * a.o_bstride + col;
     float bv[VN];
 #pragma unroll
@@ -428,25 +556,9 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
       float acc[VN];
 #pragma unroll
       for (int k = 0; k < VN; ++k) acc[k] = 0.0f;
-      for (int e0 = 0; e0 < rec.z; e0 += U) {
-        const int n = min(U, rec.z - e0);
-        const uint32_t mp = msgs + uint32_t(rec.y + e0) * 8u;
-        uint2 m[U];
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (u < n) m[u] = lds_u2(mp + u * 8u);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (u < n) v[u] = lds_v4(stage + m[u].x * slab_bytes);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (u < n) {
-            float f[VN];
-            Vec16<T>::unpack(v[u], f);
-            axpy_exact<T, VN>(acc, __uint_as_float(m[u].y), f);
-          }
-      }
+      // (measured: a separate unpredicated path for full batches of U messages is slower, 139 -> 145 us at cfg 2)
+      for (int e0 = 0; e0 < rec.z; e0 += U)
+        reduce_batch<T, U>(acc, msgs + uint32_t(rec.y + e0) * 8u, stage, slab_bytes, min(U, rec.z - e0));
       if (on)
         stg_v4(ob + int64_t(rec.x) * a.ldo, finish_reg<T, VN>(acc, bv, a.bias != nullptr, a.relu));
     }
@@ -456,6 +568,8 @@ __global__ void __launch_bounds__(512, 1) k_agg_tiled(const __grid_constant__ CU
       if (rem == per_tile - 1) mbar_arrive(smem_u32(&mempty_bar[seq & 1]));
     }
     if (++st == ns) { st = 0; ++st_round; }
+    if (++slab == a.slabs) { slab = 0; ++b; }
+    if (++rem == per_tile) { rem = 0; b = 0; ++seq; }
   }
 }
 
@@ -469,6 +583,16 @@ inline int env_int(const char* name, int dflt, int lo, int hi) {
 }
 inline int tiled_threads_hint() {
   static int v = env_int("GWEN_TILED_THREADS", 512, 64, 512) / 32 * 32;
+  return v;
+}
+// gather mode of locality plans: GWEN_GATHER_MODE 1 = cp.async per 16 bytes, 2 = one bulk copy per row slab;
+// GWEN_GATHER_WARPS = producer warps of mode 1
+inline int gather_mode_hint() {
+  static int v = env_int("GWEN_GATHER_MODE", 1, 1, 2);
+  return v;
+}
+inline int gather_warps_hint() {
+  static int v = env_int("GWEN_GATHER_WARPS", 2, 1, 4);
   return v;
 }
 inline int num_stages_hint() {
@@ -890,7 +1014,12 @@ extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const void* 
   // chunks; slab_elems is an upper bound that is halved until two stages fit.
   const int64_t rows = int64_t(plan->max_tile_runs) * plan->run_len;
   const size_t rec_bytes = align_up(size_t(plan->max_tile_rows) * 16, 128);
-  const size_t meta_bytes = rec_bytes + align_up(size_t(plan->max_tile_msgs + 2) * 8, 128);
+  // gather mode: single-row runs copied by cp.async; the tile's run list travels with the metadata
+  // (run_start then needs 4 readable entries past run_ptr[num_tiles]: GWEN_PLAN_GATHER promises them)
+  const bool gather = plan->run_len == 1 && (plan->reserved & GWEN_PLAN_GATHER);
+  GWEN_CHECK_ARG(!gather || ldx * esz < (int64_t(1) << 32), "row pitch must be below 4 GB");
+  const size_t runs_off = rec_bytes + align_up(size_t(plan->max_tile_msgs + 2) * 8, 128);
+  const size_t meta_bytes = runs_off + (gather ? align_up(size_t(plan->max_tile_runs + 8) * 4, 128) : 0);
   const size_t smem_cap = 226 * 1024;
   auto smem_for = [&](int lpr_, int ns_) {
     return size_t(ns_) * size_t(rows) * lpr_ * 16 + 2 * meta_bytes + 256;
@@ -917,7 +1046,9 @@ extern "C" int gwen_aggregate_tiled_fwd(const gwen_tile_plan* plan, const void* 
               feat, ldo, o_bstride, tile_count, tile_begin, static_cast<int>(ceil_div(feat, slab)), slab,
               plan->run_len, (epilogue & GWEN_EPI_RELU) ? 1 : 0,
               static_cast<uint32_t>(stage_bytes), static_cast<uint32_t>(rec_bytes),
-              static_cast<uint32_t>(meta_bytes), ns};
+              static_cast<uint32_t>(meta_bytes), ns, gather ? gather_mode_hint() : 0, gather_warps_hint(), x, ldx,
+              x_bstride,
+              static_cast<uint32_t>(runs_off)};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = tiled_threads_hint();
   if (dtype == GWEN_F32) {

@@ -84,15 +84,15 @@ class TilePlan:
     """Device arrays of a tile plan + the host struct handed to gwen_aggregate_tiled_fwd."""
 
     def __init__(self, order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, n_dst, run_len,
-                 max_tile_runs, max_tile_rows, max_tile_msgs, total_runs, total_src):
+                 max_tile_runs, max_tile_rows, max_tile_msgs, total_runs, total_src, flags: int = 0):
         self.order, self.tile_ptr, self.run_ptr, self.run_start = order, tile_ptr, run_ptr, run_start
         self.trec, self.tmsg, self.tmsg_base = trec, tmsg, tmsg_base
         self.num_tiles = tile_ptr.numel() - 1
         self.n_dst, self.run_len, self.max_tile_runs = n_dst, run_len, max_tile_runs
         self.max_tile_rows, self.max_tile_msgs = max_tile_rows, max_tile_msgs
-        self.total_runs, self.total_src = total_runs, total_src
+        self.total_runs, self.total_src, self.flags = total_runs, total_src, flags
         self.struct = _lib.TilePlanStruct(self.num_tiles, run_len, max_tile_runs, max_tile_rows,
-                                          max_tile_msgs, 0, n_dst, _ptr(tile_ptr), _ptr(run_ptr),
+                                          max_tile_msgs, flags, n_dst, _ptr(tile_ptr), _ptr(run_ptr),
                                           _ptr(run_start), _ptr(trec), _ptr(tmsg), _ptr(tmsg_base))
 
     @property
@@ -239,7 +239,67 @@ class GraphCSR:
         self._plans[key] = plan
         return plan
 
-    def _build_plan(self, order, tile_ptr, run_len: int) -> TilePlan:
+    # -- locality tiles (graphs whose numbering carries no locality) ------------------------------
+    LOCALITY_TARGET_ROWS = 150      # mean cell size aimed for (a cell of ~150 nodes stages ~1.35 rows per row on a mesh)
+    LOCALITY_MERGE_ROWS, LOCALITY_CAP_ROWS = 160, 256
+    LOCALITY_MAX_AMPLIFICATION = 2.5
+
+    def locality_tiles(self, radius: int, rounds: int = 12, merge_rows: Optional[int] = None,
+                       cap_rows: Optional[int] = None, deal: Optional[int] = None):
+        """``gwen_locality_tiles`` on this graph: ``(order, tile_ptr, cell, depth, status)`` with
+        ``status = [cells, tiles, largest cell, unreached nodes]`` read back (one host sync)."""
+        merge_rows = merge_rows or self.LOCALITY_MERGE_ROWS
+        cap_rows = cap_rows or self.LOCALITY_CAP_ROWS
+        L, st, dev, n = lib(), _stream(), self.device, self.n_dst
+        if deal is None:   # the grid of the staged kernel: one persistent CTA per SM
+            deal = torch.cuda.get_device_properties(dev).multi_processor_count
+        with torch.cuda.device(dev):
+            need = C.c_size_t()
+            check(L.gwen_locality_workspace_bytes(n, C.byref(need)), "gwen_locality_workspace_bytes")
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            order = torch.empty(n, dtype=torch.int32, device=dev)
+            tile_ptr = torch.empty(n + 2, dtype=torch.int32, device=dev)
+            cell = torch.empty(n, dtype=torch.int32, device=dev)
+            depth = torch.empty(n, dtype=torch.int32, device=dev)
+            status = torch.zeros(4, dtype=torch.int32, device=dev)
+            check(L.gwen_locality_tiles(_ptr(self.rowptr), _ptr(self.src), n, radius, rounds, merge_rows, cap_rows,
+                                        deal, _ptr(order), _ptr(tile_ptr), _ptr(cell), _ptr(depth), _ptr(status),
+                                        _ptr(ws), need.value, st), "gwen_locality_tiles")
+            stat = status.tolist()
+            tile_ptr = tile_ptr[:stat[1] + 1].clone()
+        return order, tile_ptr, cell, depth, stat
+
+    def locality_plan(self, radius: Optional[int] = None) -> Optional[TilePlan]:
+        """Tile plan over locality tiles (csrc/locality.cu), single-row runs copied by the gather producer of
+        the tiled kernel; memoised.  ``radius=None`` searches the seed spacing whose mean cell size is nearest
+        LOCALITY_TARGET_ROWS (cell size grows with the square of the radius on a surface mesh; at most four
+        tries).  Returns None when the graph has no locality to exploit (staged rows per destination row above
+        LOCALITY_MAX_AMPLIFICATION: an expander, a dense graph) -- the row kernel serves those."""
+        key = ("locality", radius)
+        if key in self._plans:
+            return self._plans[key]
+        plan = None
+        if self.n_src == self.n_dst and self.n_dst >= 2 and self.num_messages > 0:
+            if radius is not None:
+                order, tile_ptr = self.locality_tiles(radius)[:2]
+            else:
+                tried, r = {}, 8
+                while r not in tried and len(tried) < 4:
+                    res = self.locality_tiles(r)
+                    tried[r] = res
+                    mean = self.n_dst / max(1, res[4][0])
+                    r = int(min(64, max(1, round(r * (self.LOCALITY_TARGET_ROWS / mean) ** 0.5))))
+                best = min(tried, key=lambda q: abs(self.n_dst / max(1, tried[q][4][0]) - self.LOCALITY_TARGET_ROWS))
+                order, tile_ptr = tried[best][:2]
+                self.locality_radius = best
+                del tried
+            plan = self._build_plan(order, tile_ptr, 1, flags=_lib.PLAN_GATHER)
+            if plan.amplification > self.LOCALITY_MAX_AMPLIFICATION:
+                plan = None
+        self._plans[key] = plan
+        return plan
+
+    def _build_plan(self, order, tile_ptr, run_len: int, flags: int = 0) -> TilePlan:
         L, st = lib(), _stream()
         dev = self.device
         nt = tile_ptr.numel() - 1
@@ -261,10 +321,11 @@ class GraphCSR:
                                          _ptr(tmsg_base), _ptr(status), _ptr(ws), need.value, st),
                   "gwen_tile_plan_build")
             total_runs, max_runs, total_src, max_msgs, max_rows = status.tolist()[:5]  # one-time sync
-            run_start = run_full[:total_runs].clone()
+            run_start = torch.zeros(total_runs + 4, dtype=torch.int32, device=dev)   # 4 readable entries of padding
+            run_start[:total_runs].copy_(run_full[:total_runs])
             del run_full, ws
         return TilePlan(order, tile_ptr, run_ptr, run_start, trec, tmsg, tmsg_base, self.n_dst,
-                        run_len, max_runs, max_rows, max_msgs, total_runs, total_src)
+                        run_len, max_runs, max_rows, max_msgs, total_runs, total_src, flags)
 
 
 def _build(edge_index: torch.Tensor, num_nodes: int, flags: int,

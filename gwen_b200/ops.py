@@ -30,7 +30,14 @@ _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
 #   "auto"    stencil on a plain or masked mesh with 16-byte rows; tiled for any other graph whose nodes
 #             are numbered like a grid (2-D tile plans: improved=True meshes, partition-local graphs)
 #             when the plan fits in shared memory; else rows
+#   "locality" staged kernel over locality tiles (GraphCSR.locality_plan): graphs whose numbering carries no
+#             locality; bitwise equal to "rows".  "auto" takes it for sparse graphs of >= LOCALITY_MIN_NODES nodes
+#             that are not grid-numbered, and falls back to rows when the graph has no locality
 DEFAULT_AGG_KERNEL = "auto"
+import os as _os
+LOCALITY_TILES = _os.environ.get("GWEN_LOCALITY_TILES", "1") != "0"
+LOCALITY_MIN_NODES = 32768        # below this the row kernel's working set sits in L2 anyway
+LOCALITY_MAX_DEGREE = 32          # mean messages per destination above which a tile's sources cannot fit
 
 
 def dtype_code(dt: torch.dtype) -> int:
@@ -107,6 +114,12 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
         elif graph.grid_shape is not None and graph.n_src == graph.n_dst and (f * esz) % 16 == 0 and \
                 plan is None and tile_range is None:
             kernel = "tiled_or_rows"
+        elif LOCALITY_TILES and graph.grid_shape is None and graph.n_src == graph.n_dst and \
+                (f * esz) % 16 == 0 and plan is None and tile_range is None and \
+                graph.n_dst >= LOCALITY_MIN_NODES and graph.num_messages <= LOCALITY_MAX_DEGREE * graph.n_dst:
+            # a large sparse graph whose numbering is not a grid's: compact tiles found from the CSR
+            # (GraphCSR.locality_plan, once per graph) + the staged kernel's row-gather producer
+            kernel = "locality_or_rows"
         else:
             kernel = "rows"
     bias32 = _bias32(bias)
@@ -114,6 +127,20 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
         if out is None:
             out = torch.empty((b, graph.n_dst, f), dtype=x3.dtype, device=x3.device)
         epi = _lib.EPI_RELU if relu else _lib.EPI_NONE
+        if kernel in ("locality", "locality_or_rows"):
+            lplan = plan if plan is not None else graph.locality_plan()
+            rc = _lib.GWEN_E_NOSUPPORT
+            if lplan is not None:
+                rc = lib().gwen_aggregate_tiled_fwd(C.byref(lplan.struct), _ptr(x3), _ptr(out), b, n_src, f, f,
+                                                    n_src * f, f, graph.n_dst * f, code, _ptr(bias32), epi, slab,
+                                                    0, 0, _stream())
+            if rc == _lib.GWEN_E_NOSUPPORT and kernel == "locality_or_rows":
+                kernel = "rows"     # no locality in this graph, or its tiles do not fit in shared memory
+            elif lplan is None:
+                raise RuntimeError("this graph has no locality plan (GraphCSR.locality_plan() is None)")
+            else:
+                check(rc, "gwen_aggregate_tiled_fwd")
+                return out.reshape(tuple(lead) + (graph.n_dst, f))
         if kernel == "tiled_or_rows":
             # the TMA-staged kernel (bitwise equal to "rows", ~2x faster on grid-numbered graphs) unless
             # its stages do not fit in shared memory for this width

@@ -135,13 +135,16 @@ int gwen_aggregate_fwd(const int32_t* rowptr, const int32_t* src, const float* w
  *   tmsg_base int32[num_tiles+1]  first message of each tile in tmsg
  * All arrays are caller-allocated device memory (run_start capacity = E' is always enough;
  * trec and tmsg 16-byte aligned).  The result is bitwise identical to gwen_aggregate_fwd. */
+#define GWEN_PLAN_GATHER 1 /* gwen_tile_plan.reserved: run_len == 1 and run_start has >= 4 readable entries
+                             past its last run -> source rows are copied one by one with 16-byte cp.async by
+                             the producer warp (tiles of gwen_locality_tiles) instead of one TMA box per run */
 typedef struct gwen_tile_plan {
   int32_t num_tiles;
   int32_t run_len;         /* rows per run = TMA box height (<= 256)                        */
   int32_t max_tile_runs;   /* largest run_ptr[t+1] - run_ptr[t]; sizes the data stages      */
   int32_t max_tile_rows;   /* most destination rows in a tile                               */
   int32_t max_tile_msgs;   /* most staged messages of a tile (status[3])                    */
-  int32_t reserved;
+  int32_t reserved;        /* flags: GWEN_PLAN_GATHER                                        */
   int64_t n_dst;
   const int32_t* tile_ptr;  /* device */
   const int32_t* run_ptr;   /* device */
@@ -167,6 +170,26 @@ int gwen_tile_plan_build(const int32_t* rowptr, const int32_t* src, const float*
 int gwen_uniform_tiles(int64_t n_dst, int32_t tile_rows, int32_t* tile_ptr_out, void* stream);
 int gwen_grid_tiles(int64_t height, int64_t width, int32_t th, int32_t tw, int32_t* order_out,
                     int32_t* tile_ptr_out, void* stream);
+/* Locality tiles (csrc/locality.cu) for a graph whose node numbering carries no locality (a mesh with permuted
+ * ids, an unstructured grid in file order): compact patches of the graph found from the CSR alone -- seeds = a
+ * maximal independent set of the radius-th power of the graph (`rounds` Luby rounds with hashed priorities),
+ * cells = their Voronoi regions (multi-source BFS), order = nodes sorted by (cell, BFS depth, id); cells above
+ * cap_rows are cut into equal chunks, consecutive cells are packed into one tile while it stays within merge_rows.
+ * Replaces nothing in the reference (PyG's scatter_add has no locality pass); it is the north_star's "one-time
+ * CSR/dst-sorted graph preprocessor" extended so the TMA/shared-memory staged kernel serves such graphs.
+ *   order    int32[n]      out: processing order (a permutation of 0..n-1)
+ *   tile_ptr int32[n + 2]  out: tile t covers positions tile_ptr[t] .. tile_ptr[t+1]; status[1] tiles are written
+ *   cell, depth int32[n]   out: cell index and BFS depth of every node
+ *   status   int32[4]      [0] cells, [1] tiles, [2] largest cell, [3] nodes no seed reached (asymmetric edge lists;
+ *                          they share one extra cell)
+ * deal > 0: the tiles are renumbered by size -- descending row count, dealt in snake order over `deal` CTAs -- because
+ * the staged kernel gives tile t to CTA t mod grid (pass the grid it will run with, the SM count); 0 keeps cell order.
+ * Deterministic; no host synchronisation.  Feed order / tile_ptr to gwen_tile_plan_build with run_len = 1 and set
+ * GWEN_PLAN_GATHER in the plan. */
+int gwen_locality_workspace_bytes(int64_t n, size_t* bytes_out_host);
+int gwen_locality_tiles(const int32_t* rowptr, const int32_t* src, int64_t n, int32_t radius, int32_t rounds,
+                        int32_t merge_rows, int32_t cap_rows, int32_t deal, int32_t* order, int32_t* tile_ptr, int32_t* cell,
+                        int32_t* depth, int32_t* status, void* ws, size_t ws_bytes, void* stream);
 /* slab_elems: feature columns staged per work item: 8, 16 or 32 sixteen-byte chunks
  * (0 = widest that fits); two stages of max_tile_runs * run_len * slab bytes must fit in the
  * 227 KB of shared memory, else GWEN_E_NOSUPPORT (use gwen_aggregate_fwd). */
