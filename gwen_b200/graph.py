@@ -240,8 +240,8 @@ class GraphCSR:
         return plan
 
     # -- locality tiles (graphs whose numbering carries no locality) ------------------------------
-    LOCALITY_TARGET_ROWS = 150      # mean cell size aimed for (a cell of ~150 nodes stages ~1.35 rows per row on a mesh)
-    LOCALITY_MERGE_ROWS, LOCALITY_CAP_ROWS = 160, 256
+    LOCALITY_TARGET_ROWS = 200      # mean cell size aimed for (a cell of ~200 nodes stages ~1.4 rows per row on a mesh)
+    LOCALITY_MERGE_ROWS, LOCALITY_CAP_ROWS = 200, 256
     LOCALITY_MAX_AMPLIFICATION = 2.5
 
     def locality_tiles(self, radius: int, rounds: int = 12, merge_rows: Optional[int] = None,
