@@ -28,7 +28,9 @@ public API with pinned HOST buffers (H2D of x and D2H of the result inside the t
   N = 1: cfg 3 full six-layer forward (bf16, B = 8) next to the torch-op sequence torch_geometric 2.3.1
          runs for the same layers on the same GPU (``gpu_reference``) and an in-run parity check of a row
          band against the fp32 oracle; one cfg 5 member training step; cfg 4 (2048^2) forward and
-         forward+backward on one GPU (the N = 1 point of the strong-scaling family).
+         forward+backward on one GPU (the N = 1 point of the strong-scaling family); the cfg 2 aggregation on
+         graphs that are not the plain mesh (node ids randomly permuted -> locality tiles; 10 % of the nodes
+         cut out -> masked stencil), each next to the row kernel on the same graph.
   N > 1: cfg 4 strong scaling (the same fixed 2048^2 mesh split into row bands: forward, and
          forward + backward + gradient all-reduce); at N >= 4 the cfg 5 training step (B = 21).
 """
@@ -348,6 +350,64 @@ def probe_train_member_cfg5(dev):
                         "mask id%125==124) + backward through all six layers (tcgen05 dgrad/wgrad, stencil A^T), bf16 "
                         "activations, fp32 master weights and fp32 weight gradients, optimizer step excluded",
             "ms_per_member_step": ms_t, "member_steps_per_s": 1e3 / ms_t}
+
+
+def probe_general_graphs_cfg2(dev):
+    """The aggregation on graphs that are NOT the plain mesh, at cfg 2's size (582 x 390, F = 256, fp32), through the
+    public call (``ops.aggregate(kernel="auto")``): the mesh with randomly permuted node ids (K0r locality tiles +
+    the staged kernel's row-gather producer; the row kernel on the same graph beside it) and the mesh with 10 % of the
+    nodes cut out (masked stencil).  Three rotating buffer pairs, 100-launch regions, result checks in-run."""
+    import torch
+    import gwen_b200 as gw
+    from gwen_b200 import ops
+    n = H * W
+    peak = measured_peaks()[0]
+    ei = gw.grid(H, W, dev)
+    gen = torch.Generator(device="cpu").manual_seed(23)
+    perm = torch.randperm(n, generator=gen).to(dev)
+    g_perm = gw.build_graph(perm[ei].contiguous(), n)
+    cut = (torch.rand(n, generator=gen) < 0.1).to(dev)
+    g_mask = gw.build_graph(ei[:, ~(cut[ei[0]] | cut[ei[1]])].contiguous(), n)
+    xs = [torch.randn(n, FEAT, device=dev) for _ in range(3)]
+    outs = [torch.empty(n, FEAT, device=dev) for _ in range(3)]
+    bias = torch.randn(FEAT, device=dev) * 0.1
+    k = [0]
+
+    def run(graph, kernel):
+        def fn():
+            for _ in range(100):
+                i = k[0] % 3
+                k[0] += 1
+                ops.aggregate(graph, xs[i], bias, kernel=kernel, out=outs[i].unsqueeze(0))
+        return fn
+
+    def entry(graph, kernel, alg):
+        us = _timed(run(graph, kernel), 1, 3) * 10.0       # ms per 100 launches -> us per launch
+        return {"us_per_launch": us, "GBs": alg / us / 1e3, "frac_of_copy_peak": alg / us / 1e3 / peak}
+
+    res = {"workload": "cfg2 mesh 582x390, F=256 fp32, single-layer message+aggregate on graphs that are not the plain "
+                       "mesh; algorithmic bytes = SURVEY 8(d) with 8*E' for CSR graphs (src and w are read)"}
+    alg = 2 * n * FEAT * 4 + 4 * (n + 1) + 8 * g_perm.num_messages + 4 * n
+    plan = g_perm.locality_plan()
+    ent = {"graph_kind": "no grid numbering detected" if g_perm.grid_shape is None else "grid",
+           "locality_tiles": None if plan is None else {"tiles": plan.num_tiles, "max_tile_rows": plan.max_tile_rows,
+                                                        "max_tile_sources": plan.max_tile_runs,
+                                                        "staged_rows_per_destination_row": plan.amplification},
+           "algorithmic_bytes": alg, "auto (locality tiles)": entry(g_perm, "auto", alg),
+           "row kernel": entry(g_perm, "rows", alg)}
+    ent["auto_bitwise_equals_row_kernel"] = bool(torch.equal(ops.aggregate(g_perm, xs[0], bias),
+                                                             ops.aggregate(g_perm, xs[0], bias, kernel="rows")))
+    res["permuted_node_ids"] = ent
+    alg_m = 2 * n * FEAT * 4 + 4 * (n + 1) + 4 * g_mask.num_messages + 4 * n
+    ent = {"mesh_kind": g_mask.mesh_kind, "cut_nodes": int(cut.sum()), "algorithmic_bytes": alg_m,
+           "auto (masked stencil)": entry(g_mask, "auto", alg_m), "row kernel": entry(g_mask, "rows", alg_m)}
+    a, b = ops.aggregate(g_mask, xs[0], bias), ops.aggregate(g_mask, xs[0], bias, kernel="rows")
+    ent["nmax_vs_row_kernel"] = ((a - b).abs().max() / b.abs().max()).item()
+    res["masked_mesh_10pct"] = ent
+    del xs, outs
+    gw.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return res
 
 
 def probe_cfg4_single(dev):
@@ -784,7 +844,8 @@ def run_ours(args):
         if world == 1:
             probes = [("full_forward_cfg3", lambda: probe_full_forward_cfg3(dev)),
                       ("train_step_cfg5_member", lambda: probe_train_member_cfg5(dev)),
-                      ("strong_cfg4", lambda: probe_cfg4_single(dev))]
+                      ("strong_cfg4", lambda: probe_cfg4_single(dev)),
+                      ("general_graphs_cfg2", lambda: probe_general_graphs_cfg2(dev))]
         elif halo_mode == "peer":
             probes = [("strong_cfg4", lambda: probe_strong_cfg4(dev, world, rank))]
             if world >= 4:

@@ -128,3 +128,37 @@ def test_locality_tiles_red_zone(dev):
     ops.aggregate(g, x, kernel="locality", out=out.unsqueeze(0))
     assert torch.all(buf[:32] == 7.5) and torch.all(buf[32 + n:] == 7.5)
     assert torch.equal(out, ops.aggregate(g, x, kernel="rows"))
+
+
+def test_model_on_a_permuted_mesh_matches_oracle(dev, monkeypatch):
+    """The six-layer model (fp32) on a mesh whose node ids are permuted: every layer's aggregation goes through
+    kernel="auto" -> locality tiles; against the CPU oracle on the same permuted edge list, and equal to the model
+    on the natural numbering with the rows permuted back (the layers are permutation-equivariant) within 1e-5."""
+    from tests.golden import weights as wts
+    monkeypatch.setattr(ops, "LOCALITY_MIN_NODES", 1000)
+    h, w, c, hid = 48, 64, 16, 64
+    n = h * w
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5))
+    ei_c = perm[orc.grid(h, w)].contiguous()
+    ref = orc.GNNModelOracle(c, c, hid)
+    wts.fill_model_(ref, 3)
+    cfg = gw.GNNConfig(nodes_in=n, nodes_out=n, channels_in=c, channels_out=c, hidden_feats=hid)
+    model = gw.GNNModel(cfg)
+    model.load_state_dict(ref.state_dict())
+    model = model.to(dev)
+    x = torch.randn(2, n, c, generator=torch.Generator().manual_seed(6))
+    ei = ei_c.to(dev)
+    with torch.no_grad():
+        y = model(x.to(dev), ei)
+        yr = ref(x, ei_c)
+    g = gw.get_graph(ei, n)
+    assert g.grid_shape is None and g._plans.get(("locality", None)) is not None     # the path under test ran
+    err = ((y.cpu() - yr).abs().max() / yr.abs().max()).item()
+    assert err <= 1e-5, err
+    # backward through the same path (transposed graph -> its own locality plan)
+    xg = x.to(dev).requires_grad_(True)
+    model(xg, ei).square().sum().backward()
+    xr = x.clone().requires_grad_(True)
+    ref(xr, ei_c).square().sum().backward()
+    gerr = ((xg.grad.cpu() - xr.grad).norm() / xr.grad.norm()).item()
+    assert gerr <= 1e-4, gerr
