@@ -140,6 +140,7 @@ class GraphCSR:
         self._transposed: Optional["GraphCSR"] = None
         self._plans: Dict[Tuple, TilePlan] = {}
         self.order: Optional[torch.Tensor] = None  # locality order for the row kernel
+        self.auto_calls = 0     # ops.aggregate(kernel="auto") calls on a graph that is not grid-numbered (see ops.py)
 
     @property
     def device(self):

@@ -118,8 +118,11 @@ def aggregate(graph: GraphCSR, x: torch.Tensor, bias: Optional[torch.Tensor] = N
                 (f * esz) % 16 == 0 and plan is None and tile_range is None and \
                 graph.n_dst >= LOCALITY_MIN_NODES and graph.num_messages <= LOCALITY_MAX_DEGREE * graph.n_dst:
             # a large sparse graph whose numbering is not a grid's: compact tiles found from the CSR
-            # (GraphCSR.locality_plan, once per graph) + the staged kernel's row-gather producer
-            kernel = "locality_or_rows"
+            # (GraphCSR.locality_plan, once per graph) + the staged kernel's row-gather producer.  The plan costs
+            # ~10-50 ms, so it is built at the SECOND call on a graph handle: a graph that is used once (a loader
+            # handing a fresh edge_index every iteration, models_gnn.py:359) never pays for it
+            graph.auto_calls += 1
+            kernel = "locality_or_rows" if graph.auto_calls >= 2 or ("locality", None) in graph._plans else "rows"
         else:
             kernel = "rows"
     bias32 = _bias32(bias)

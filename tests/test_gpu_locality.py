@@ -102,14 +102,18 @@ def test_auto_picks_locality_tiles_and_falls_back(dev, monkeypatch):
     g = gw.build_graph(ei, n)
     x = torch.randn(n, 128, device=dev)
     monkeypatch.setattr(ops, "LOCALITY_MIN_NODES", 1000)
-    y = ops.aggregate(g, x)                       # auto -> locality tiles
+    y0 = ops.aggregate(g, x)                      # first call on a graph handle: row kernel, no plan is built
+    assert ("locality", None) not in g._plans
+    y = ops.aggregate(g, x)                       # second call: auto -> locality tiles
     assert ("locality", None) in g._plans and g._plans[("locality", None)] is not None
+    assert torch.equal(y0, y)
     assert torch.equal(y, ops.aggregate(g, x, kernel="rows"))
     # a graph without locality (random edges): the plan is refused, auto falls back to the row kernel
     torch.manual_seed(9)
     er = orc.erdos_renyi_graph(2000, 0.01).to(dev)
     g2 = gw.build_graph(er, 2000)
     x2 = torch.randn(2000, 64, device=dev)
+    ops.aggregate(g2, x2)
     y2 = ops.aggregate(g2, x2)
     assert g2._plans[("locality", None)] is None
     assert torch.equal(y2, ops.aggregate(g2, x2, kernel="rows"))
