@@ -15,9 +15,9 @@ so = os.path.join(ROOT, "gwen_b200", "libgwen_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 pat = re.compile(r"\b(UTC[A-Z]*MMA|LDTM|STTM|UTCBAR|UTMALDG|UTMASTG|UBLKCP|UTMAPF|UTMACCTL|UCGABAR_ARV|UCGABAR_WAIT|"
                  r"FFMA2|FADD2|FMUL2|HMNMX2|SYNCS|FENCE\.VIEW\.ASYNC|LDG\.E[.0-9A-Z]*\.SYS|STG\.E[.0-9A-Z]*\.SYS|"
-                 r"RED\.E[.0-9A-Z]*|ATOM[.0-9A-Z]*)\b")
+                 r"RED\.E[.0-9A-Z]*|ATOM[.0-9A-Z]*|LDGSTS[.0-9A-Z]*|LDGSTSBAR[.0-9A-Z]*)\b")
 want = ("k_linear_tc3", "k_gcn_fused", "k_wgrad_tc", "k_linear_tf32x3", "k_wgrad_tf32x3", "k_grid_stencil", "k_agg_tiled",
-        "k_linear_tc2")
+        "k_linear_tc2", "k_linear_b2b")
 cur, funcs = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
