@@ -166,3 +166,21 @@ def test_model_on_a_permuted_mesh_matches_oracle(dev, monkeypatch):
     ref(xr, ei_c).square().sum().backward()
     gerr = ((xg.grad.cpu() - xr.grad).norm() / xr.grad.norm()).item()
     assert gerr <= 1e-4, gerr
+
+
+def test_triangular_cells_unstructured_numbering(dev):
+    """An ICON-like graph (triangular cells, three neighbours each) in a random numbering: the radius search finds
+    tiles with few staged rows per row, the tiles are bit-exact vs the restatement, the aggregation is bitwise equal
+    to the row kernel."""
+    from tests.graphs import tri_mesh_edges
+    h, w = 60, 80
+    n = 2 * h * w
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(8))
+    ei = perm[tri_mesh_edges(h, w)].contiguous().to(dev)
+    g = gw.build_graph(ei, n)
+    assert g.grid_shape is None
+    _check_tiles_vs_oracle_deal(g, 12, 12, 200, 256, 148)
+    plan = g.locality_plan()
+    assert plan is not None and g.locality_radius > 8 and plan.amplification < 1.5
+    x = torch.randn(2, n, 128, device=dev)
+    assert torch.equal(ops.aggregate(g, x, kernel="locality"), ops.aggregate(g, x, kernel="rows"))

@@ -44,7 +44,15 @@ def timeit(fn, iters=200, warm=10):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-ei = gw.grid(h, w, dev)
+tri = os.environ.get("GWEN_BENCH_TRI") == "1"     # triangular cells (three neighbours), same node count
+if tri:
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests.graphs import tri_mesh_edges
+    h, w = 291, 390
+    ei = tri_mesh_edges(h, w).to(dev)
+    n = 2 * h * w
+else:
+    ei = gw.grid(h, w, dev)
 g = torch.Generator(device="cpu").manual_seed(23)
 perm = torch.randperm(n, generator=g).to(dev)
 eip = perm[ei].contiguous()
@@ -56,7 +64,7 @@ plan = gp.locality_plan(radius or None)
 torch.cuda.synchronize()
 t_plan = time.time() - t0
 msgs = gp.num_messages
-res = {"mesh": "%dx%d, node ids randomly permuted" % (h, w), "feat": f, "messages": msgs, "peak_gbs": peak,
+res = {"mesh": ("triangular cells of a %dx%d lattice (3 neighbours), node ids randomly permuted" if tri else "%dx%d, node ids randomly permuted") % (h, w), "feat": f, "messages": msgs, "peak_gbs": peak,
        "locality_plan": None if plan is None else {
            "radius": radius or getattr(gp, "locality_radius", None), "tiles": plan.num_tiles,
            "max_tile_rows": plan.max_tile_rows, "max_tile_sources": plan.max_tile_runs,
