@@ -28,7 +28,8 @@ int linear_tc_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t
 int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldw,
                               int64_t lddx, const void* dy, const void* w, const void* dx);
 int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
-                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st);
+                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st,
+                         const void* mask = nullptr, int64_t ldm = 0);
 
 int linear_tc_batched_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
                                 int64_t x_bstride, int64_t y_bstride, const void* x, const void* w,
@@ -455,6 +456,23 @@ extern "C" int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx
   GemmArgs g{dy, weight, dx, nullptr, m, k, n_out, lddy, ldw, lddx, n_out, 0, 0};
   return dtype == GWEN_F32 ? launch_gemm<float, true, false, false>(g, 1, st)
                            : launch_gemm<__nv_bfloat16, true, false, false>(g, 1, st);
+}
+
+// dx = (dy W) * (mask > 0): the dgrad with the previous layer's ReLU backward folded into the GEMM epilogue
+// (tcgen05 CTA-pair kernel only; GWEN_E_NOSUPPORT otherwise -- the caller then runs gwen_linear_bwd_data +
+// gwen_relu_bias_bwd, which give the same bits)
+extern "C" int gwen_linear_bwd_data_masked(const void* dy, const void* weight, void* dx, const void* mask,
+                                           int64_t m, int64_t k, int64_t n_out, int64_t lddy, int64_t ldw,
+                                           int64_t lddx, int64_t ldmask, int dtype, void* stream) {
+  GWEN_CHECK_ARG(m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  GWEN_CHECK_ARG(dy && weight && dx && mask, "null pointer");
+  GWEN_CHECK_ARG(lddy >= n_out && ldw >= k && lddx >= k && ldmask >= k, "row pitch too small");
+  if (dtype != GWEN_BF16 || m == 0 || k == 0 || ldmask % 8 || (reinterpret_cast<uintptr_t>(mask) & 15u) ||
+      !linear_tc_dgrad_supported(m, k, n_out, lddy, ldw, lddx, dy, weight, dx))
+    return set_err(GWEN_E_NOSUPPORT, "masked dgrad runs on the bf16 tcgen05 pair kernel only");
+  return linear_tc_dgrad_bf16(dy, weight, dx, m, k, n_out, lddy, ldw, lddx, static_cast<cudaStream_t>(stream), mask,
+                              ldmask);
 }
 
 extern "C" int gwen_linear_batched_fwd(const void* x, const void* weight, void* y, int64_t batch, int64_t m,

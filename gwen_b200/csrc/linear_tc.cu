@@ -30,7 +30,7 @@ int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn);
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
                         int b_mn, cudaStream_t st, int64_t batch = 1, int64_t x_bstride = 0,
-                        int64_t y_bstride = 0);
+                        int64_t y_bstride = 0, const void* mask = nullptr, int64_t ldm = 0, int64_t m_bstride = 0);
 
 namespace {
 
@@ -416,8 +416,9 @@ int linear_tc_dgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t ld
   return linear_tc3_supported(m, n_out, k_in, 1);
 }
 int linear_tc_dgrad_bf16(const void* dy, const void* w, void* dx, int64_t m, int64_t k_in,
-                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st) {
-  return linear_tc3_fwd_bf16(dy, w, dx, m, n_out, k_in, lddy, ldw, lddx, nullptr, 0, 1, st);
+                         int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, cudaStream_t st,
+                         const void* mask, int64_t ldm) {
+  return linear_tc3_fwd_bf16(dy, w, dx, m, n_out, k_in, lddy, ldw, lddx, nullptr, 0, 1, st, 1, 0, 0, mask, ldm, 0);
 }
 
 // batch-strided forward / dgrad in ONE launch (bf16, CTA-pair kernel); 0 = not served

@@ -51,12 +51,32 @@ struct Tc3Args {
   uint32_t wait_ns;  // poll interval of the epilogue warps waiting for an accumulator (0 = spin)
 };
 
+__device__ __forceinline__ uint4 lds_v4_tc3(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+// 0xffff per bf16 half of `y2` that is > 0 (one HSET2.BF16; k_relu_bias_bwd's integer rule "sign clear and magnitude
+// non-zero" gives the same mask for every value a ReLU can output)
+__device__ __forceinline__ uint32_t gt0_mask(uint32_t y2) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&y2), __floats2bfloat162_rn(0.0f, 0.0f));
+}
+
+// kMask (round 2): the dgrad with the ReLU backward of the PREVIOUS layer folded in -- the output tile is multiplied
+// by (mask > 0) elementwise, mask = a bf16 tensor of the output's shape (the layer input = the previous layer's ReLU
+// output).  Per 32-column sub-chunk the mask tile is brought by ONE TMA load (same box and swizzle as the store) into
+// the staging buffer the output will be packed into, one chunk ahead (two staging buffers per warp); each thread
+// reads back the 64 bytes of its row, ANDs its packed bf16 pairs with the compare mask and overwrites them.
+// Measured (512->1024 dgrad, M = 896 292, plain kernel 751 us): this form with an integer compare per half 1105 us;
+// + the operand producer prefetching the next tile's mask block into L2 (UTMAPF) 1145 us; per-thread 16-byte
+// read-only loads of the mask row instead of the TMA tile 1164 us.
+template <bool kMask>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
     k_linear_tc3(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-                 const __grid_constant__ CUtensorMap ymap, Tc3Args g) {
+                 const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap mmap, Tc3Args g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full_bar[2],
-      tmem_empty_bar[2];
+      tmem_empty_bar[2], mask_bar[kMask ? 2 * kEpiWarps : 1];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t rank = cluster_ctarank();
@@ -105,6 +125,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[i]), epi_arrivals);
+    }
+    if constexpr (kMask) {
+      tma_prefetch_desc(&mmap);
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(smem_u32(&mask_bar[i]), 1);
     }
     mbar_fence_init();
   }
@@ -187,7 +211,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
     const uint32_t empty_remote0 = mapa_u32(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_remote1 = mapa_u32(smem_u32(&tmem_empty_bar[1]), 0);
     uint32_t seq = 0, buf = 0;
+    [[maybe_unused]] uint32_t mseq = 0;   // chunks this warp has masked: buffer mseq & 1, barrier phase (mseq >> 1) & 1
     if (g4 < n_sub && g4 < g.epi_groups) {
+      if constexpr (kMask) {   // prologue: the first chunk's mask tile
+        if (lane == 0 && my_tiles > 0) {
+          int fmb, fnt;
+          tile_of(0, fmb, fnt);
+          const uint32_t mb_addr = smem_u32(&mask_bar[(warp - 2) * 2]);
+          mbar_expect_tx(mb_addr, 2048u);
+          tma_load_3d(my_stage, &mmap, fnt * g.bn + g4 * 32, int(fmb % mb_per_batch) * (2 * BM) + int(rank) * BM + q * 32,
+                      int(fmb / mb_per_batch), mb_addr);
+        }
+      }
       for (int64_t idx = 0; idx < my_tiles; ++idx, ++seq) {
         int mb, nt;
         tile_of(idx, mb, nt);
@@ -251,6 +286,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           const int c = sc * 32;
           uint32_t r[32];
           tmem_ld32_nowait(t_addr + uint32_t(c), r);
+          if constexpr (kMask) {
+            // mask tile of THIS chunk is in flight into staging buffer `buf` (issued one chunk ago, or by the
+            // prologue); the OTHER buffer's store (previous chunk) must have been read before the next chunk's mask
+            // tile lands in it
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              int64_t nidx = idx;
+              int nsc = sc + g.epi_groups;
+              if (nsc >= n_sub) { nsc = g4; ++nidx; }
+              if (nidx < my_tiles) {
+                int nmb, nnt;
+                tile_of(nidx, nmb, nnt);
+                const uint32_t nb = buf ^ 1u;
+                const uint32_t mb_addr = smem_u32(&mask_bar[(warp - 2) * 2 + int(nb)]);
+                mbar_expect_tx(mb_addr, 2048u);
+                tma_load_3d(my_stage + nb * 2048u, &mmap, nnt * g.bn + nsc * 32,
+                            int(nmb % mb_per_batch) * (2 * BM) + int(rank) * BM + q * 32, int(nmb / mb_per_batch), mb_addr);
+              }
+            }
+          } else
           // the staging buffer we are about to overwrite must have been read by its TMA store
           if (lane == 0) {
             if (g.bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -266,6 +321,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
           const uint32_t sbuf = my_stage + buf * 2048u + row_off;
           // bias slice of this sub-chunk (same address for every lane: broadcast LDS.128)
           const float4* bp = reinterpret_cast<const float4*>(bias_s + n0 + c);
+          if constexpr (kMask) {   // the chunk's mask tile has landed in the buffer we are about to pack into
+            mbar_wait(smem_u32(&mask_bar[(warp - 2) * 2 + int(buf)]), (mseq >> 1) & 1u);
+            ++mseq;
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {  // 4 chunks of 8 columns = 16 bytes
             const float4 b0 = bp[2 * j], b1 = bp[2 * j + 1];
@@ -274,6 +333,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
             o.y = bias_pack(r[8 * j + 2], r[8 * j + 3], b0.z, b0.w, relu);
             o.z = bias_pack(r[8 * j + 4], r[8 * j + 5], b1.x, b1.y, relu);
             o.w = bias_pack(r[8 * j + 6], r[8 * j + 7], b1.z, b1.w, relu);
+            if constexpr (kMask) {
+              const uint4 mk = lds_v4_tc3(sbuf + ((uint32_t(j) ^ sw) << 4));
+              o.x &= gt0_mask(mk.x);
+              o.y &= gt0_mask(mk.y);
+              o.z &= gt0_mask(mk.z);
+              o.w &= gt0_mask(mk.w);
+            }
             sts_v4(sbuf + ((uint32_t(j) ^ sw) << 4), o);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -308,7 +374,8 @@ int linear_tc3_supported(int64_t m, int64_t k, int64_t n_out, int b_mn) {
 
 int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_t k, int64_t n_out,
                         int64_t ldx, int64_t ldw, int64_t ldy, const float* bias, int relu,
-                        int b_mn, cudaStream_t st, int64_t batch, int64_t x_bstride, int64_t y_bstride) {
+                        int b_mn, cudaStream_t st, int64_t batch, int64_t x_bstride, int64_t y_bstride,
+                        const void* mask, int64_t ldm, int64_t m_bstride) {
   if (batch < 1 || batch > 65535) return set_err(GWEN_E_BADARG, "batch out of range");
   int bn = 0;
   for (int c : {256, 128, 64})
@@ -329,14 +396,15 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
     const char* v = getenv("GWEN_TC3_BUFS");
     return v ? atoi(v) : 0;
   }();
-  const int bufs = (bufs_env == 1 || bufs_env == 2) ? bufs_env : ((k <= 128 || n_out <= 64) ? 2 : 1);
+  const int bufs = mask ? 2 : ((bufs_env == 1 || bufs_env == 2) ? bufs_env : ((k <= 128 || n_out <= 64) ? 2 : 1));
   // deep reductions are MMA-bound and want ring depth (6 stages need the room of 8 staging buffers);
   // shallow ones are store-bound and want all 16 epilogue warps
   static const int groups_env = [] {
     const char* v = getenv("GWEN_TC3_EPI_GROUPS");
     return v ? atoi(v) : 0;
   }();
-  const int epi_groups = (groups_env == 2 || groups_env == 4) ? groups_env : (k >= 512 ? 2 : 4);
+  // (masked dgrad: the epilogue does more per chunk and wants all 16 warps -- 512->1024 998 -> 936 us)
+  const int epi_groups = (groups_env == 2 || groups_env == 4) ? groups_env : ((k >= 512 && !mask) ? 2 : 4);
   // 64-column chunks (128-byte store rows) only for the narrow output tile (bn = 64: one chunk per warp).  Measured
   // at M = 896 292 (round 2, 32 / 64 columns): 64->1024 0.359 / 0.416 ms, 256->512 0.283 / 0.342, 1024->64 0.390 / 0.369
   // -- the wider chunk serialises two TMEM loads per store and costs a ring stage; the store row width was not the limit.
@@ -344,12 +412,17 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
     const char* v = getenv("GWEN_TC3_EPI_COLS");
     return v ? atoi(v) : 0;
   }();
-  const int epi_cols = (cols_env == 32 || cols_env == 64) ? (bn % cols_env ? 32 : cols_env)
-                                                          : (epi_groups == 4 && bn == 64 ? 64 : 32);
+  const int epi_cols = mask ? 32 : ((cols_env == 32 || cols_env == 64) ? (bn % cols_env ? 32 : cols_env)
+                                                                       : (epi_groups == 4 && bn == 64 ? 64 : 32));
   rc = epi_cols == 64
            ? make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B)
            : make_tensor_map_3d(&ymap, y, GWEN_BF16, n_out, m, batch, ldy, y_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc != GWEN_OK) return rc;
+  CUtensorMap mmap = ymap;
+  if (mask) {
+    rc = make_tensor_map_3d(&mmap, mask, GWEN_BF16, n_out, m, batch, ldm, m_bstride, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != GWEN_OK) return rc;
+  }
   const size_t staging_bytes = size_t(4 * epi_groups) * bufs * (epi_cols == 64 ? 4096 : 2048) + align_up(size_t(n_out) * 4, 1024);
   static const int stage_cap = [] {
     const char* v = getenv("GWEN_TC3_STAGES");
@@ -368,9 +441,15 @@ int linear_tc3_fwd_bf16(const void* x, const void* w, void* y, int64_t m, int64_
   // measured at the GWEN shapes (M = 896 292): both orders within 3 %; round-robin is the default
   const int row_major = order_env >= 0 ? order_env : 0;
   Tc3Args g{bias, m, static_cast<int>(n_out), k_blocks, bn, stages, relu, bufs, row_major, epi_groups, static_cast<int>(batch), b_mn, epi_cols, wait_backoff_ns()};
-  GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
-  k_linear_tc3<<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, g);
+  if (mask) {
+    GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    k_linear_tc3<true><<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, mmap, g);
+  } else {
+    GWEN_CUDA(cudaFuncSetAttribute(k_linear_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    k_linear_tc3<false><<<2 * pairs, kTc3Threads, smem, st>>>(amap, bmap, ymap, mmap, g);
+  }
   GWEN_LAUNCH_CHECK("k_linear_tc3");
   return GWEN_OK;
 }

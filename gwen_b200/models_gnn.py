@@ -19,7 +19,7 @@ from torch import nn
 
 from .graph import GraphCSR, get_graph
 from . import ops
-from .nn import GCNConv, b2b_fusable, gcn_conv_b2b_project, gcn_conv_pair, pair_fusable
+from .nn import GCNConv, ReluLink, b2b_fusable, gcn_conv_b2b_project, gcn_conv_pair, pair_fusable
 
 __all__ = ["GNNConfig", "DownConvLayers", "UpConvLayers", "GCNConvLayers", "GNNModel", "loss_func"]
 
@@ -46,6 +46,9 @@ class DownConvLayers(nn.Module):
         self.conv5 = GCNConv(h // 8, h // 16)
 
     def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
+        # training: the ReLU backward of conv1 and conv2 rides in the dgrad epilogue of the layer after it
+        # (nn.ReluLink; bf16 tcgen05 path only, same bits as the unfused backward)
+        l1, l2 = ReluLink(), ReluLink()
         if x.is_cuda and x.dtype == torch.bfloat16:
             # inference on a large mesh (both bitwise equal to the layers run one by one):
             #  * conv1 and conv2's projection back to back in one kernel (gwen_b200.nn.gcn_conv_b2b_project): conv1's
@@ -57,7 +60,7 @@ class DownConvLayers(nn.Module):
                 p2 = gcn_conv_b2b_project(x, graph, self.conv1, self.conv2)
                 x2_like = p2
             else:
-                x = self.conv1(x, edge_index, relu=True)
+                x = self.conv1(x, edge_index, relu=True, link_out=l1)
                 x2_like = x
             if pair_fusable(graph, x2_like, self.conv2, self.conv3):
                 return gcn_conv_pair(x if p2 is None else None, graph, self.conv2, self.conv3, relu_b=True, p=p2)
@@ -65,9 +68,9 @@ class DownConvLayers(nn.Module):
                 x = ops.aggregate(graph, p2, self.conv2.bias, True)
                 return self.conv3(x, edge_index, relu=True)
         else:
-            x = self.conv1(x, edge_index, relu=True)
-        x = self.conv2(x, edge_index, relu=True)
-        x = self.conv3(x, edge_index, relu=True)
+            x = self.conv1(x, edge_index, relu=True, link_out=l1)
+        x = self.conv2(x, edge_index, relu=True, link_in=l1, link_out=l2)
+        x = self.conv3(x, edge_index, relu=True, link_in=l2)
         return x
 
 
@@ -89,8 +92,9 @@ class UpConvLayers(nn.Module):
             graph = edge_index if isinstance(edge_index, GraphCSR) else get_graph(edge_index, x.size(-2))
             p5 = gcn_conv_b2b_project(x, graph, self.upconv4, self.upconv5)
             return ops.aggregate(graph, p5, self.upconv5.bias, False)
-        x = self.upconv4(x, edge_index, relu=True)
-        x = self.upconv5(x, edge_index)
+        l4 = ReluLink()
+        x = self.upconv4(x, edge_index, relu=True, link_out=l4)
+        x = self.upconv5(x, edge_index, link_in=l4)
         return x
 
 

@@ -22,7 +22,24 @@ from torch import Tensor
 from . import ops
 from .graph import GraphCSR, get_graph
 
-__all__ = ["GCNConv", "gcn_conv", "gcn_conv_pair", "pair_fusable", "b2b_fusable", "gcn_conv_b2b_project"]
+__all__ = ["GCNConv", "ReluLink", "gcn_conv", "gcn_conv_pair", "pair_fusable", "b2b_fusable", "gcn_conv_b2b_project"]
+
+
+class ReluLink:
+    """Hand-over between two consecutive layers of a CHAIN  y = conv_b(relu(conv_a(x)))  in training: when conv_b's
+    backward produces dx with its dgrad GEMM it folds conv_a's ReLU backward into that kernel's epilogue
+    (``ops.linear_bwd_data_masked``, mask = conv_b's input = conv_a's ReLU output) and sets ``masked``; conv_a's
+    backward then skips its own mask pass (read dy, read y, write dz -> only the bias-gradient sums of dy remain).
+    Only for chains: conv_a's output must have no other consumer (the model code wires it, reference
+    models_gnn.py:147-149,204-206 is such a chain).  Same bits as the unfused backward."""
+    __slots__ = ("masked",)
+
+    def __init__(self):
+        self.masked = False
+
+
+import os as _os0
+BWD_MASK_FUSION = _os0.environ.get("GWEN_BWD_MASK_FUSION", "1") != "0"
 
 
 class _GCNConvFn(torch.autograd.Function):
@@ -30,7 +47,8 @@ class _GCNConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], graph: GraphCSR,
-                relu: bool, agg_first: bool):
+                relu: bool, agg_first: bool, link_in: Optional[ReluLink] = None,
+                link_out: Optional[ReluLink] = None):
         fused = agg_first and ops.gcn_fused_preferred(graph, x, weight)
         if fused:          # (A_hat x) W^T in ONE kernel: the aggregated rows never leave the SM
             y = ops.gcn_fused(graph, x, weight, bias, relu)
@@ -44,6 +62,7 @@ class _GCNConvFn(torch.autograd.Function):
             y = ops.aggregate(graph, h, bias, relu)
             saved_in = x
         ctx.graph, ctx.relu, ctx.agg_first, ctx.fused = graph, relu, agg_first, fused
+        ctx.link_in, ctx.link_out = link_in, (link_out if relu else None)
         ctx.has_bias = bias is not None
         ctx.save_for_backward(saved_in, weight, y if relu else None)
         return y
@@ -52,8 +71,12 @@ class _GCNConvFn(torch.autograd.Function):
     def backward(ctx, dy: Tensor):
         saved_in, weight, y = ctx.saved_tensors
         graph_t = ctx.graph.transposed()
-        # ReLU mask and bias gradient in one pass over dy (out of place: autograd owns dy)
-        dy, db = ops.relu_bias_bwd(dy.contiguous(), y if ctx.relu else None, ctx.has_bias)
+        # ReLU mask and bias gradient in one pass over dy (out of place: autograd owns dy); when the next layer's
+        # dgrad epilogue has already applied this layer's mask (ReluLink) only the bias-gradient sums remain
+        masked = ctx.link_out is not None and ctx.link_out.masked
+        if masked:
+            ctx.link_out.masked = False
+        dy, db = ops.relu_bias_bwd(dy.contiguous(), y if (ctx.relu and not masked) else None, ctx.has_bias)
         if db is not None:
             db = db.to(weight.dtype)
         need_dx = ctx.needs_input_grad[0]
@@ -68,16 +91,21 @@ class _GCNConvFn(torch.autograd.Function):
             dh = ops.aggregate(graph_t, dy)                       # A_hat^T dy
             dw = ops.linear_bwd_weight(dh, saved_in)              # dW = dh^T x
             if need_dx:
-                dx = ops.linear_bwd_data(dh, weight)
-        return dx, dw.to(weight.dtype), db, None, None, None
+                if ctx.link_in is not None and BWD_MASK_FUSION:   # x = relu(previous layer): its mask in our epilogue
+                    dx = ops.linear_bwd_data_masked(dh, weight, saved_in)
+                    ctx.link_in.masked = dx is not None
+                if dx is None:
+                    dx = ops.linear_bwd_data(dh, weight)
+        return dx, dw.to(weight.dtype), db, None, None, None, None, None
 
 
 def gcn_conv(x: Tensor, graph: GraphCSR, weight: Tensor, bias: Optional[Tensor] = None,
-             relu: bool = False, agg_first: Optional[bool] = None) -> Tensor:
-    """Functional form on a prebuilt graph handle."""
+             relu: bool = False, agg_first: Optional[bool] = None, link_in: Optional[ReluLink] = None,
+             link_out: Optional[ReluLink] = None) -> Tensor:
+    """Functional form on a prebuilt graph handle.  ``link_in`` / ``link_out``: see :class:`ReluLink`."""
     if agg_first is None:
         agg_first = weight.shape[1] < weight.shape[0]
-    return _GCNConvFn.apply(x, weight, bias, graph, relu, agg_first)
+    return _GCNConvFn.apply(x, weight, bias, graph, relu, agg_first, link_in, link_out)
 
 
 # Cross-layer fusion (inference): two consecutive layers  y = epi_b(conv_b(relu(conv_a(x))))  where conv_a
@@ -204,7 +232,8 @@ class GCNConv(torch.nn.Module):
         self._cached_graph = None
 
     def forward(self, x: Tensor, edge_index, edge_weight: Optional[Tensor] = None,
-                relu: bool = False) -> Tensor:
+                relu: bool = False, link_in: Optional[ReluLink] = None,
+                link_out: Optional[ReluLink] = None) -> Tensor:
         if edge_weight is not None:
             raise NotImplementedError("edge_weight is not used on the GWEN path")
         if not x.is_cuda:
@@ -217,7 +246,7 @@ class GCNConv(torch.nn.Module):
             graph = get_graph(edge_index, x.size(-2), self.add_self_loops, self.improved)
             if self.cached:
                 self._cached_graph = graph
-        return gcn_conv(x, graph, self.lin.weight, self.bias, relu)
+        return gcn_conv(x, graph, self.lin.weight, self.bias, relu, link_in=link_in, link_out=link_out)
 
     def propagate(self, edge_index, x: Tensor, add_bias: bool = True, relu: bool = False) -> Tensor:
         """Message + aggregate only (PyG ``MessagePassing.propagate`` with GCN's message): gathers

@@ -17,7 +17,7 @@ from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
 __all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred",
-           "linear", "linear_b2b", "linear_b2b_supported", "linear_bwd_data", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
+           "linear", "linear_b2b", "linear_b2b_supported", "linear_bwd_data", "linear_bwd_data_masked", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
            "rows_gather", "rows_scatter_", "dtype_code", "clear_cast_cache"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
@@ -416,6 +416,29 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
         check(lib().gwen_linear_bwd_data_ws(_ptr(dy2), _ptr(wt), _ptr(dx), dy2.shape[0], k, n_out, n_out,
                                             k, k, dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
               "gwen_linear_bwd_data")
+    return dx.reshape(tuple(dy.shape[:-1]) + (k,))
+
+
+def linear_bwd_data_masked(dy: torch.Tensor, weight: torch.Tensor, mask: torch.Tensor) -> Optional[torch.Tensor]:
+    """``(dy @ weight) * (mask > 0)`` in ONE kernel (``gwen_linear_bwd_data_masked``: the previous layer's ReLU
+    backward in the dgrad epilogue), ``mask`` = the layer input (bf16, shape of the result).  Returns None when the
+    fused kernel does not serve the problem (not bf16, shapes outside the tcgen05 pair kernel): the caller then runs
+    ``linear_bwd_data`` and leaves the mask to the previous layer's ``relu_bias_bwd`` -- the same bits."""
+    n_out, k = weight.shape
+    if dy.dtype != torch.bfloat16 or mask.dtype != torch.bfloat16 or mask.shape[-1] != k:
+        return None
+    dy2 = dy.reshape(-1, n_out).contiguous()
+    m2 = mask.reshape(-1, k)
+    if m2.shape[0] != dy2.shape[0] or not m2.is_contiguous():
+        return None
+    wt = _cast_cached(weight, dy2.dtype)
+    with torch.cuda.device(dy2.device):
+        dx = torch.empty((dy2.shape[0], k), dtype=dy2.dtype, device=dy2.device)
+        rc = lib().gwen_linear_bwd_data_masked(_ptr(dy2), _ptr(wt), _ptr(dx), _ptr(m2), dy2.shape[0], k, n_out, n_out,
+                                               k, k, k, dtype_code(dy2.dtype), _stream())
+    if rc == _lib.GWEN_E_NOSUPPORT:
+        return None
+    check(rc, "gwen_linear_bwd_data_masked")
     return dx.reshape(tuple(dy.shape[:-1]) + (k,))
 
 

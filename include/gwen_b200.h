@@ -323,6 +323,13 @@ int gwen_linear_fwd_ws(const void* x, const void* weight, void* y, int64_t m, in
 int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m, int64_t k,
                          int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int dtype,
                          void* stream);
+/* The same with the PREVIOUS layer's ReLU backward folded into the epilogue: dx = (dy W) * (mask > 0), mask = a bf16
+ * tensor of dx's shape (the layer input x, i.e. the previous layer's ReLU output; replaces the `torch.relu` backward
+ * between two GCNConv calls, reference models_gnn.py:147-149,204-206).  bf16 on the tcgen05 CTA-pair kernel only:
+ * GWEN_E_NOSUPPORT otherwise, and gwen_linear_bwd_data + gwen_relu_bias_bwd give the same bits. */
+int gwen_linear_bwd_data_masked(const void* dy, const void* weight, void* dx, const void* mask, int64_t m, int64_t k,
+                                int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int64_t ldmask, int dtype,
+                                void* stream);
 /* Batched forms: `batch` independent row blocks x[b] = x + b * x_bstride ([m, k], row pitch ldx) against the
  * SAME weight, results to y[b] = y + b * y_bstride -- e.g. the owned rows of a band buffer per ensemble
  * member.  bf16 problems the CTA-pair kernel takes run as ONE launch (the batch index is the third TMA

@@ -517,3 +517,54 @@ def test_mixed_precision_training_sees_fused_adam_updates(dev):
     assert not torch.equal(ya, y0)                          # the cached bf16 weights were refreshed
     assert nmax(ya.float(), yb.float()) <= 2e-2             # same trajectory as torch.optim.Adam (bf16 activations)
     gw.clear_graph_cache()
+
+
+# ---------------------------------------------------------------------------------------------
+# ReLU backward folded into the dgrad epilogue (gwen_linear_bwd_data_masked, nn.ReluLink)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n_out", [(4096, 1024, 512), (5000, 512, 256), (3333, 1024, 64), (70000, 512, 1024)])
+def test_masked_dgrad_equals_dgrad_then_relu_bwd(dev, m, k, n_out):
+    """dx = (dy W) * (mask > 0) from ONE kernel is bitwise what gwen_linear_bwd_data + the ReLU mask pass give
+    (ragged M, the three GWEN dgrad shapes that feed a ReLU layer, mask values incl. +0, -0 and negatives)."""
+    torch.manual_seed(m)
+    dy = torch.randn(m, n_out, device=dev).bfloat16()
+    w = (torch.randn(n_out, k, device=dev) * 0.05)
+    y = torch.relu(torch.randn(m, k, device=dev)).bfloat16()
+    y[::7, ::3] = -0.0
+    y[1::5, 1::4] = -1.5                      # not a ReLU output, but the rule is "> 0"
+    fused = ops.linear_bwd_data_masked(dy, w, y)
+    assert fused is not None, "the masked dgrad must run on the tcgen05 pair kernel for this shape"
+    plain = ops.linear_bwd_data(dy, w)
+    ref, _ = ops.relu_bias_bwd(plain, y, False)
+    assert torch.equal(fused, ref)
+    assert torch.equal(fused == 0, (ref == 0))
+    # red zone: nothing outside the result
+    assert fused.shape == (m, k)
+
+
+def test_model_backward_with_relu_links_is_bitwise_the_unfused_backward(dev, monkeypatch):
+    """Six-layer bf16 model, hid = 1024 (the real widths), forward + backward: with the ReLU masks of conv1, conv2 and
+    upconv4 folded into the next layer's dgrad epilogue every gradient equals the unfused backward bit for bit
+    (bias gradients: same values summed by another kernel -> 1e-6)."""
+    from gwen_b200 import nn as gnn
+    h, w, c, hid, b = 64, 96, 64, 1024, 1
+    n = h * w
+    ref, model = _real_width_pair(11, n, dev)
+    ei = orc.grid(h, w).to(dev)
+    x = torch.randn(b, n, c, generator=torch.Generator().manual_seed(4)).to(dev).bfloat16()
+    grads = {}
+    for fused in (True, False):
+        monkeypatch.setattr(gnn, "BWD_MASK_FUSION", fused)
+        for p in model.parameters():
+            p.grad = None
+        xg = x.clone().requires_grad_(True)
+        model(xg, ei).float().square().sum().backward()
+        grads[fused] = ([p.grad.clone() for p in model.parameters() if p.grad is not None], xg.grad.clone())
+    assert torch.equal(grads[True][1], grads[False][1])
+    assert len(grads[True][0]) == len(grads[False][0]) > 0
+    for (name, p), ga, gb in zip([(k_, v) for k_, v in model.named_parameters() if v.grad is not None],
+                                 grads[True][0], grads[False][0]):
+        if name.endswith("bias"):
+            assert l2err(ga, gb) <= 1e-6, name
+        else:
+            assert torch.equal(ga, gb), name
