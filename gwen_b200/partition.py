@@ -439,7 +439,10 @@ class _BandGCNFn(torch.autograd.Function):
         gs = None
         if not ctx.agg_first:   # dz is what gets aggregated: write it straight into its band buffer
             gs = net.buffer(("b", li), b, weight.shape[0], dy.dtype)
-        dz, db = ops.relu_bias_bwd(dy, y if ctx.relu else None, ctx.has_bias,
+        # the next layer's dgrad epilogue may already have applied this layer's ReLU mask (see nn.ReluLink): then only
+        # the bias-gradient sums (and the copy into the band buffer) remain
+        masked = ctx.relu and net._masked.pop(li, False)
+        dz, db = ops.relu_bias_bwd(dy, y if (ctx.relu and not masked) else None, ctx.has_bias,
                                    out=None if gs is None else band.owned(gs))
         need_dx = ctx.needs_input_grad[0]
         dx = None
@@ -466,7 +469,13 @@ class _BandGCNFn(torch.autograd.Function):
                 ops.linear_bwd_data(dz, weight, out=band.owned(gs))
                 dx = band.aggregate(gs)
             else:
-                dx = ops.linear_bwd_data(dh, weight)
+                from . import nn as _nn
+                if li > 0 and net.layers[li - 1][1] and _nn.BWD_MASK_FUSION:   # x = relu(layer li - 1): its mask here
+                    dx = ops.linear_bwd_data_masked(dh, weight, saved_in)
+                    if dx is not None:
+                        net._masked[li - 1] = True
+                if dx is None:
+                    dx = ops.linear_bwd_data(dh, weight)
         return dx, dw, db, None, None, None, None
 
 
@@ -490,6 +499,7 @@ class BandGNNModel(torch.nn.Module):
         self._flat = None
         self._views = {}
         self._pending = {}
+        self._masked = {}       # li -> True: layer li's ReLU mask was applied by layer li + 1's dgrad epilogue
         d, u = model.conv_layers.down_conv_layers, model.conv_layers.up_conv_layers
         self.layers = [(d.conv1, True), (d.conv2, True), (d.conv3, True),
                        (u.upconv3, True), (u.upconv4, True), (u.upconv5, False)]

@@ -41,6 +41,7 @@ def test_band_model_two_gpus():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4 and out["loss_rel_err"] < 1e-5
+    assert out["bf16_mask_fusion_bitwise"] is True
 
 
 @pytest.mark.gpu
@@ -58,3 +59,4 @@ def test_band_model_single_rank():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
     assert out["forward_bitwise_equal"] is True and out["grad_max_rel_err"] < 1e-4 and out["loss_rel_err"] < 1e-5
+    assert out["bf16_mask_fusion_bitwise"] is True

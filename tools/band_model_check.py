@@ -105,6 +105,40 @@ def main():
     res["forward_bitwise_equal"] = bool(okt[0].item())
     res["grad_max_rel_err"] = -okt[1].item()
     ok = res["forward_bitwise_equal"] and res["grad_max_rel_err"] < 1e-4
+    # ---- bf16: the ReLU masks folded into the next layer's dgrad epilogue (nn.ReluLink logic of the band model) on
+    # vs off: the same gradients bit for bit (weights; biases: the same values summed by the same kernel) ------------
+    from gwen_b200 import nn as gnn
+    h2, w2, c2, hid2, b2 = 16 * world + 5, 64, 64, 256, 2
+    n2 = h2 * w2
+    cfg2 = gw.GNNConfig(nodes_in=n2, nodes_out=n2, channels_in=c2, channels_out=c2, hidden_feats=hid2)
+    model2 = gw.GNNModel(cfg2).to(dev).to(torch.bfloat16)
+    g2 = gw.get_graph(gw.grid(h2, w2, dev), n2)
+    band2 = partition.PeerMeshBand(h2, w2, g2.dis)
+    net2 = partition.BandGNNModel(model2, band2)
+    xo2 = torch.randn(b2, band2.n_own, c2, device=dev, generator=gen).to(torch.bfloat16)
+    to2 = torch.randn(b2, band2.n_own, c2, device=dev, generator=gen)
+    got, used = {}, {}
+    old_flag = gnn.BWD_MASK_FUSION
+    for fused in (True, False):
+        gnn.BWD_MASK_FUSION = fused
+        for p in model2.parameters():
+            p.grad = None
+        (net2(xo2).float() * to2).sum().backward()
+        used[fused] = len(net2._masked)            # flags are consumed by the producer layers: 0 left after backward
+        net2.allreduce_grads()
+        got[fused] = [(nm, p.grad.clone()) for nm, p in model2.named_parameters() if p.grad is not None]
+    gnn.BWD_MASK_FUSION = old_flag
+    same = used[True] == 0 and len(got[True]) == len(got[False]) > 0
+    for (nm, ga), (_, gb) in zip(got[True], got[False]):
+        if nm.endswith("bias"):
+            same &= bool(((ga.float() - gb.float()).norm() <= 1e-6 * gb.float().norm().clamp_min(1e-30)).item())
+        else:
+            same &= bool(torch.equal(ga, gb))
+    st = torch.tensor([1.0 if same else 0.0], device=dev)
+    dist.all_reduce(st, op=dist.ReduceOp.MIN)
+    res["bf16_mask_fusion_bitwise"] = bool(st.item())
+    ok = ok and res["bf16_mask_fusion_bitwise"]
+    del model2, net2, band2
     # ---- strong-scaling timings -------------------------------------------------------------------
     if not args.no_time:
         del model, net, band
