@@ -361,7 +361,10 @@ int launch_stencil(const CUtensorMap& xmap, const StencilArgs& a, size_t smem, c
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  // developer measurement only (GWEN_PEER_NO_COOP=1): the same grid without the cooperative attribute, to see what
+  // the co-residency guarantee costs per launch; never the default -- without it a partly scheduled grid would spin
+  static const bool no_coop = getenv("GWEN_PEER_NO_COOP") != nullptr;
+  cfg.numAttrs = no_coop ? 0 : 1;
   GWEN_CUDA(cudaLaunchKernelEx(&cfg, kern, xmap, a));
   GWEN_LAUNCH_CHECK("k_grid_stencil (peer)");
   return GWEN_OK;
