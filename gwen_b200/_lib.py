@@ -119,6 +119,8 @@ PROTOTYPES = {
     "gwen_linear_bwd_data_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _sz, _p]),
     "gwen_linear_bwd_weight": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p,
                                       _sz, _p]),
+    "gwen_linear_bwd_weight_bias_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
+    "gwen_linear_bwd_weight_bias": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _sz, _p]),
     "gwen_linear_bwd_weight_workspace_bytes": (_int, [_i64, _i64, _i64, C.POINTER(_sz)]),
     "gwen_relu_bwd": (_int, [_p, _p, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_bias_grad": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _sz, _p]),

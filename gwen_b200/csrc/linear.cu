@@ -49,9 +49,9 @@ int linear_tf32x3_dgrad(const void* dy, const void* w, void* dx, int64_t m, int6
 // linear_wgrad_tc.cu
 int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
                               const void* dy, const void* x);
-int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out);
+int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out, int with_db = 0);
 int linear_tc_wgrad_bf16(const void* dy, const void* x, float* part, int64_t m, int64_t k_in,
-                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st);
+                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st, float* dbpart = nullptr);
 
 // linear_wgrad_tf32x3.cu
 int linear_wgrad_tf32x3_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t lddy, int64_t ldx,
@@ -546,6 +546,44 @@ extern "C" int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int6
   if (k % 64 == 0 && n_out % 64 == 0 && m >= 256) splits = std::max(splits, linear_tc_wgrad_splits(m, k, n_out));
   if (k % 4 == 0 && n_out % 4 == 0 && m >= 4096) splits = std::max(splits, linear_wgrad_tf32x3_splits(m, k, n_out));
   *out = static_cast<size_t>(splits) * n_out * k * sizeof(float) + 256;
+  return GWEN_OK;
+}
+
+// dW AND db = column sums of dy from the same pass (bf16 tcgen05 wgrad only: ones-column MMA, k_wgrad_tc<kDb>)
+extern "C" int gwen_linear_bwd_weight_bias_workspace_bytes(int64_t m, int64_t k, int64_t n_out, size_t* out) {
+  GWEN_CHECK_ARG(out && m >= 0 && k >= 0 && n_out >= 0, "bad arguments");
+  const int splits = (k % 64 == 0 && n_out % 64 == 0 && m >= 256) ? linear_tc_wgrad_splits(m, k, n_out, 1) : 1;
+  *out = static_cast<size_t>(splits) * n_out * (k + 1) * sizeof(float) + 512;
+  return GWEN_OK;
+}
+
+extern "C" int gwen_linear_bwd_weight_bias(const void* dy, const void* x, float* dw, float* db, int64_t m, int64_t k,
+                                           int64_t n_out, int64_t lddy, int64_t ldx, int64_t lddw, int dtype,
+                                           void* ws, size_t ws_bytes, void* stream) {
+  GWEN_CHECK_ARG(m >= 0 && k >= 0 && n_out >= 0, "negative size");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  GWEN_CHECK_ARG(dy && x && dw && db && ws, "null pointer");
+  GWEN_CHECK_ARG(lddy >= n_out && ldx >= k && lddw >= k, "row pitch too small");
+  // K tiles of 256 columns fill tensor memory (2 x 256 accumulator columns): the bias sums would force 128-column
+  // tiles, and that costs more than the pass it saves (measured, 512 -> 1024 at M = 896 292: 787 -> 1528 us)
+  if (dtype != GWEN_BF16 || k % 256 == 0 || !linear_tc_wgrad_supported(m, k, n_out, lddy, ldx, dy, x))
+    return set_err(GWEN_E_NOSUPPORT, "wgrad with bias sums runs on the bf16 tcgen05 kernel with K tiles <= 128 only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int splits = linear_tc_wgrad_splits(m, k, n_out, 1);
+  const size_t wbytes = align_up(static_cast<size_t>(splits) * n_out * k * sizeof(float), 256);
+  const size_t need = wbytes + static_cast<size_t>(splits) * n_out * sizeof(float);
+  if (ws_bytes < need) return set_err(GWEN_E_WORKSPACE, "workspace %zu < %zu", ws_bytes, need);
+  float* part = static_cast<float*>(ws);
+  float* dbpart = reinterpret_cast<float*>(static_cast<char*>(ws) + wbytes);
+  int rc = linear_tc_wgrad_bf16(dy, x, part, m, k, n_out, lddy, ldx, st, dbpart);
+  if (rc != GWEN_OK) return rc;
+  const int64_t n_elems = n_out * k;
+  k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_elems, 256)), 256, 0, st>>>(part, splits, n_elems, n_elems, dw,
+                                                                               lddw, k);
+  GWEN_LAUNCH_CHECK("k_reduce_splits");
+  k_reduce_splits<<<static_cast<unsigned>(ceil_div(n_out, 256)), 256, 0, st>>>(dbpart, splits, n_out, n_out, db, n_out,
+                                                                             n_out);
+  GWEN_LAUNCH_CHECK("k_reduce_splits (db)");
   return GWEN_OK;
 }
 

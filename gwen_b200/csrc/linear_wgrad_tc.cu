@@ -34,11 +34,21 @@ constexpr int kWgThreads = 192;
 constexpr int kChunkBlocks = 64;   // 4096 rows per TMEM accumulation (shrink ~4e-6; 2048: 2e-6 but +15 % time)
 
 struct WgArgs {
+  float* dbpart;         // kDb: [splits][n_out] column sums of dY per split (the bias gradient's partials)
   float* part;           // [splits][n_out][k_in]
   int64_t m, per;        // rows, rows per split (multiple of RK)
   int n_out, k_in, bn, stages, tiles_j;
 };
 
+// kDb (round 2): the bias gradient db = column sums of dY out of the SAME pass -- the CTAs of the first K_in tile issue
+// one more MMA per 16 rows, dY^T times a constant tile of ones (N = 16, a 64 x 64 box of bf16 1.0 in shared memory:
+// all ones, so the 128-byte swizzle leaves it unchanged), into 16 extra TMEM columns per accumulator; the epilogue
+// adds column 0 of every finished chunk to the split's db partial.  No pass over dY for the bias gradient is left
+// when no ReLU mask has to be applied to it either (masked by the next layer's dgrad epilogue, or no ReLU).
+// Needs 2 * bn + 48 <= 512 TMEM columns: bn <= 128, i.e. K_in not a multiple of 256 (the entry point declines those:
+// forcing 128-column tiles there costs more than the pass it saves -- 512 -> 1024: 787 -> 1528 us, measured).
+// 64 -> 1024 at M = 896 292: 299 -> 345 us, and the 267 us bias-sum pass is gone.
+template <bool kDb>
 __global__ void __launch_bounds__(kWgThreads, 1)
     k_wgrad_tc(const __grid_constant__ CUtensorMap dymap, const __grid_constant__ CUtensorMap xmap,
                WgArgs g) {
@@ -55,7 +65,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   const int64_t r_begin = int64_t(split) * g.per;
   const int64_t r_end = r_begin + g.per < g.m ? r_begin + g.per : g.m;
   const int n_blocks = r_end > r_begin ? int((r_end - r_begin + RK - 1) / RK) : 0;
-  const uint32_t tmem_cols = uint32_t(2 * g.bn < 32 ? 32 : 2 * g.bn);
+  const bool db_cta = kDb && (tile % g.tiles_j) == 0;      // this CTA also reduces dY's columns
+  const uint32_t db_col0 = uint32_t(2 * g.bn);             // two 16-column db accumulators behind the dW ones
+  const uint32_t ones_addr = base + uint32_t(g.stages) * stage_bytes;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < uint32_t(2 * g.bn + (kDb ? 48 : 0))) tmem_cols *= 2;
   const int n_chunks = (n_blocks + kChunkBlocks - 1) / kChunkBlocks;
 
   if (threadIdx.x == 0) {
@@ -77,6 +91,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
                  "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if constexpr (kDb) {   // the tile of ones: generic stores, read by the tensor core (async proxy)
+    for (uint32_t o = threadIdx.x * 16u; o < box_bytes; o += kWgThreads * 16u)
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(ones_addr + o), "r"(0x3F803F80u) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -121,6 +140,14 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         for (int kk = 0; kk < RK / UMMA_K; ++kk)  // 16 rows of 128 B per UMMA_K
           umma_f16(d_addr, adesc + uint64_t(kk) * (2048 >> 4), bdesc + uint64_t(kk) * (2048 >> 4),
                    idesc, (cb | kk) ? 1u : 0u);
+        if (db_cta) {   // dY^T x ones -> 16 identical columns of column sums
+          const uint32_t idesc1 = make_idesc(16) | (1u << 15) | (1u << 16);
+          const uint64_t odesc = make_smem_desc_mn(ones_addr, box_bytes);
+#pragma unroll
+          for (int kk = 0; kk < RK / UMMA_K; ++kk)
+            umma_f16(tmem_d + db_col0 + acc * 16u, adesc + uint64_t(kk) * (2048 >> 4), odesc + uint64_t(kk) * (2048 >> 4),
+                     idesc1, (cb | kk) ? 1u : 0u);
+        }
         umma_commit(smem_u32(&empty_bar[s]));
         if (cb == kChunkBlocks - 1 || blk == n_blocks - 1) umma_commit(smem_u32(&tmem_full_bar[acc]));
       }
@@ -130,9 +157,12 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     const int q = warp & 3;
     const int i = i0 + q * 32 + lane;
     float* prow = g.part + (int64_t(split) * g.n_out + i) * g.k_in + j0;
+    float* dbp = db_cta ? g.dbpart + int64_t(split) * g.n_out + i : nullptr;
     if (n_chunks == 0) {  // empty row range: the partial tile is zero
-      if (i < g.n_out)
+      if (i < g.n_out) {
         for (int c = 0; c < g.bn; c += 4) *reinterpret_cast<uint4*>(prow + c) = make_uint4(0u, 0u, 0u, 0u);
+        if (db_cta) *dbp = 0.0f;
+      }
     }
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const uint32_t acc = uint32_t(chunk) & 1u;
@@ -156,6 +186,11 @@ __global__ void __launch_bounds__(kWgThreads, 1)
           }
         }
       }
+      if (db_cta) {   // column 0 of this chunk's 16 identical db columns (the 32-column load stays inside the allocation)
+        uint32_t r[32];
+        tmem_ld32(tmem_d + db_col0 + acc * 16u + (uint32_t(q * 32) << 16), r);
+        if (i < g.n_out) *dbp = chunk > 0 ? *dbp + __uint_as_float(r[0]) : __uint_as_float(r[0]);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
@@ -171,9 +206,9 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   }
 }
 
-int pick_bn_wg(int64_t k_in) {
+int pick_bn_wg(int64_t k_in, bool with_db = false) {
   for (int bn : {256, 128, 64})
-    if (k_in % bn == 0) return bn;
+    if (k_in % bn == 0 && !(with_db && bn > 128)) return bn;
   return 0;
 }
 
@@ -188,8 +223,8 @@ int linear_tc_wgrad_supported(int64_t m, int64_t k_in, int64_t n_out, int64_t ld
 }
 
 // number of row splits (partials) the tensor-core wgrad writes for this problem
-int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out) {
-  const int bn = pick_bn_wg(k_in);
+int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out, int with_db) {
+  const int bn = pick_bn_wg(k_in, with_db != 0);
   const int64_t tiles = ceil_div(n_out, BM) * (k_in / bn);
   int64_t s = std::max<int64_t>(1, sm_count() / tiles);
   s = std::min<int64_t>(s, std::max<int64_t>(1, m / (4 * RK)));
@@ -197,25 +232,33 @@ int linear_tc_wgrad_splits(int64_t m, int64_t k_in, int64_t n_out) {
 }
 
 int linear_tc_wgrad_bf16(const void* dy, const void* x, float* part, int64_t m, int64_t k_in,
-                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st) {
-  const int bn = pick_bn_wg(k_in);
+                         int64_t n_out, int64_t lddy, int64_t ldx, cudaStream_t st, float* dbpart) {
+  const int bn = pick_bn_wg(k_in, dbpart != nullptr);
   if (!bn) return set_err(GWEN_E_NOSUPPORT, "tcgen05 wgrad needs k_in %% 64 == 0");
   CUtensorMap dymap, xmap;
   int rc = make_tensor_map_3d(&dymap, dy, GWEN_BF16, n_out, m, 1, lddy, 0, 64, RK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
   rc = make_tensor_map_3d(&xmap, x, GWEN_BF16, k_in, m, 1, ldx, 0, 64, RK, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != GWEN_OK) return rc;
-  const int splits = linear_tc_wgrad_splits(m, k_in, n_out);
+  const int splits = linear_tc_wgrad_splits(m, k_in, n_out, dbpart != nullptr);
   const int64_t per = ceil_div(ceil_div(m, splits), RK) * RK;
   const size_t stage_bytes = size_t(2 + bn / 64) * RK * 128;
-  const int stages = static_cast<int>(std::min<size_t>(8, (224 * 1024) / stage_bytes));
-  const size_t smem = std::max<size_t>(stages * stage_bytes + 1024, 120 * 1024);  // one CTA per SM
+  const size_t ones_bytes = dbpart ? size_t(RK) * 128 : 0;
+  const int stages = static_cast<int>(std::min<size_t>(8, (224 * 1024 - ones_bytes) / stage_bytes));
+  const size_t smem = std::max<size_t>(stages * stage_bytes + ones_bytes + 1024, 120 * 1024);  // one CTA per SM
   const int tiles_j = static_cast<int>(k_in / bn);
-  WgArgs g{part, m, per, static_cast<int>(n_out), static_cast<int>(k_in), bn, stages, tiles_j};
-  GWEN_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
+  WgArgs g{dbpart, part, m, per, static_cast<int>(n_out), static_cast<int>(k_in), bn, stages, tiles_j};
   dim3 grid(static_cast<unsigned>(ceil_div(n_out, BM) * tiles_j), static_cast<unsigned>(splits));
-  k_wgrad_tc<<<grid, kWgThreads, smem, st>>>(dymap, xmap, g);
+  if (dbpart) {
+    GWEN_CUDA(cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    k_wgrad_tc<true><<<grid, kWgThreads, smem, st>>>(dymap, xmap, g);
+    GWEN_LAUNCH_CHECK("k_wgrad_tc");
+    return GWEN_OK;
+  }
+  GWEN_CUDA(cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  k_wgrad_tc<false><<<grid, kWgThreads, smem, st>>>(dymap, xmap, g);
   GWEN_LAUNCH_CHECK("k_wgrad_tc");
   return GWEN_OK;
 }

@@ -76,15 +76,27 @@ class _GCNConvFn(torch.autograd.Function):
         masked = ctx.link_out is not None and ctx.link_out.masked
         if masked:
             ctx.link_out.masked = False
-        dy, db = ops.relu_bias_bwd(dy.contiguous(), y if (ctx.relu and not masked) else None, ctx.has_bias)
-        if db is not None:
-            db = db.to(weight.dtype)
+        # no mask left to apply and the gradient goes straight into the wgrad: the bias gradient comes out of the
+        # wgrad's own pass over dy (ones-column MMA), no separate pass at all
+        db_from_wgrad = ctx.agg_first and ctx.has_bias and (masked or not ctx.relu) and BWD_MASK_FUSION \
+            and dy.dtype == torch.bfloat16
+        db = None
+        if not db_from_wgrad:
+            dy, db = ops.relu_bias_bwd(dy.contiguous(), y if (ctx.relu and not masked) else None, ctx.has_bias)
         need_dx = ctx.needs_input_grad[0]
         dx = None
         if ctx.agg_first:
             if ctx.fused:
                 saved_in = ops.aggregate(ctx.graph, saved_in)     # recompute A_hat x
-            dw = ops.linear_bwd_weight(dy, saved_in)              # dW = dy^T (A_hat x)
+            dw = None
+            if db_from_wgrad:
+                both = ops.linear_bwd_weight_bias(dy, saved_in)
+                if both is None:                                  # outside the tensor-core wgrad: the two passes
+                    dy, db = ops.relu_bias_bwd(dy.contiguous(), None, True)
+                else:
+                    dw, db = both
+            if dw is None:
+                dw = ops.linear_bwd_weight(dy, saved_in)          # dW = dy^T (A_hat x)
             if need_dx:
                 dx = ops.aggregate(graph_t, ops.linear_bwd_data(dy, weight))
         else:
@@ -96,6 +108,8 @@ class _GCNConvFn(torch.autograd.Function):
                     ctx.link_in.masked = dx is not None
                 if dx is None:
                     dx = ops.linear_bwd_data(dh, weight)
+        if db is not None:
+            db = db.to(weight.dtype)
         return dx, dw.to(weight.dtype), db, None, None, None, None, None
 
 

@@ -17,7 +17,7 @@ from ._lib import check, lib
 from .graph import GraphCSR, TilePlan, _ptr, _require_cuda, _stream
 
 __all__ = ["aggregate", "mesh_stencil", "gcn_fused", "gcn_fused_supported", "gcn_fused_preferred",
-           "linear", "linear_b2b", "linear_b2b_supported", "linear_bwd_data", "linear_bwd_data_masked", "linear_bwd_weight", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
+           "linear", "linear_b2b", "linear_b2b_supported", "linear_bwd_data", "linear_bwd_data_masked", "linear_bwd_weight", "linear_bwd_weight_bias", "relu_bwd_", "bias_grad", "relu_bias_bwd", "copy_rows_",
            "rows_gather", "rows_scatter_", "dtype_code", "clear_cast_cache"]
 
 _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
@@ -463,6 +463,36 @@ def linear_bwd_weight(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Ten
                                            dtype_code(dy2.dtype), _ptr(ws), need.value, _stream()),
               "gwen_linear_bwd_weight")
     return dw
+
+
+def linear_bwd_weight_bias(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """``(dw, db)``: :func:`linear_bwd_weight` and ``db[n] = sum_m dy[m, n]`` (fp32) out of the SAME pass over ``dy``
+    (``gwen_linear_bwd_weight_bias``: a ones-column MMA in the tcgen05 wgrad).  Returns None when the fused kernel
+    does not serve the problem (not bf16 / shapes outside the tensor-core wgrad): run ``linear_bwd_weight`` and
+    ``relu_bias_bwd`` / ``bias_grad`` instead."""
+    n_out, k = dy.shape[-1], x.shape[-1]
+    if dy.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        return None
+    dy2 = dy.reshape(-1, n_out).contiguous()
+    x2 = x.reshape(-1, k).contiguous()
+    m = dy2.shape[0]
+    with torch.cuda.device(dy2.device):
+        need = C.c_size_t()
+        check(lib().gwen_linear_bwd_weight_bias_workspace_bytes(m, k, n_out, C.byref(need)), "wgrad+bias ws")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=dy2.device)
+        if out is not None:
+            if out.dtype != torch.float32 or tuple(out.shape) != (n_out, k) or not out.is_contiguous():
+                raise ValueError("out must be a contiguous fp32 [%d, %d] tensor" % (n_out, k))
+            dw = out
+        else:
+            dw = torch.empty((n_out, k), dtype=torch.float32, device=dy2.device)
+        db = torch.empty(n_out, dtype=torch.float32, device=dy2.device)
+        rc = lib().gwen_linear_bwd_weight_bias(_ptr(dy2), _ptr(x2), _ptr(dw), _ptr(db), m, k, n_out, n_out, k, k,
+                                               dtype_code(dy2.dtype), _ptr(ws), need.value, _stream())
+    if rc == _lib.GWEN_E_NOSUPPORT:
+        return None
+    check(rc, "gwen_linear_bwd_weight_bias")
+    return dw, db
 
 
 def relu_bwd_(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:

@@ -442,8 +442,15 @@ class _BandGCNFn(torch.autograd.Function):
         # the next layer's dgrad epilogue may already have applied this layer's ReLU mask (see nn.ReluLink): then only
         # the bias-gradient sums (and the copy into the band buffer) remain
         masked = ctx.relu and net._masked.pop(li, False)
-        dz, db = ops.relu_bias_bwd(dy, y if (ctx.relu and not masked) else None, ctx.has_bias,
-                                   out=None if gs is None else band.owned(gs))
+        from . import nn as _nn
+        # nothing left to mask and dz goes straight into the wgrad: db from the wgrad's own pass (ones-column MMA)
+        db_from_wgrad = ctx.agg_first and ctx.has_bias and (masked or not ctx.relu) and _nn.BWD_MASK_FUSION \
+            and dy.dtype == torch.bfloat16
+        if db_from_wgrad:
+            dz, db = dy, None
+        else:
+            dz, db = ops.relu_bias_bwd(dy, y if (ctx.relu and not masked) else None, ctx.has_bias,
+                                       out=None if gs is None else band.owned(gs))
         need_dx = ctx.needs_input_grad[0]
         dx = None
         # weight gradient: written straight into this layer's slice of the flat fp32 gradient buffer and
@@ -452,7 +459,15 @@ class _BandGCNFn(torch.autograd.Function):
             net._deliver(li)            # an earlier backward's bucket is still in flight: deliver it first
         wv = net.grad_views(li)[0] if net.overlap_grads else None
         if ctx.agg_first:
-            dw = ops.linear_bwd_weight(dz, saved_in, out=wv)          # dW = dz^T (A_hat x)
+            dw = None
+            if db_from_wgrad:
+                both = ops.linear_bwd_weight_bias(dz, saved_in, out=wv)
+                if both is None:
+                    dz, db = ops.relu_bias_bwd(dy, None, True)
+                else:
+                    dw, db = both
+            if dw is None:
+                dw = ops.linear_bwd_weight(dz, saved_in, out=wv)      # dW = dz^T (A_hat x)
         else:
             dh = band.aggregate(gs)                                   # A_hat^T dz
             dw = ops.linear_bwd_weight(dh, saved_in, out=wv)          # dW = dh^T x
@@ -469,7 +484,6 @@ class _BandGCNFn(torch.autograd.Function):
                 ops.linear_bwd_data(dz, weight, out=band.owned(gs))
                 dx = band.aggregate(gs)
             else:
-                from . import nn as _nn
                 if li > 0 and net.layers[li - 1][1] and _nn.BWD_MASK_FUSION:   # x = relu(layer li - 1): its mask here
                     dx = ops.linear_bwd_data_masked(dh, weight, saved_in)
                     if dx is not None:

@@ -350,6 +350,14 @@ int gwen_linear_bwd_data_ws(const void* dy, const void* weight, void* dx, int64_
 int gwen_linear_bwd_weight(const void* dy, const void* x, float* dw, int64_t m, int64_t k,
                            int64_t n_out, int64_t lddy, int64_t ldx, int64_t lddw, int dtype,
                            void* ws, size_t ws_bytes, void* stream);
+/* The same AND db[n] = sum_m dy[m, n] (fp32) out of the same pass over dy: one more tcgen05.mma per 16 rows against a
+ * tile of ones in the CTAs of the first K tile.  With the ReLU mask applied by gwen_linear_bwd_data_masked this leaves
+ * no separate pass over the gradient of a layer that aggregates first.  bf16 tcgen05 kernel only (GWEN_E_NOSUPPORT
+ * otherwise); workspace from gwen_linear_bwd_weight_bias_workspace_bytes. */
+int gwen_linear_bwd_weight_bias_workspace_bytes(int64_t m, int64_t k, int64_t n_out, size_t* bytes_out_host);
+int gwen_linear_bwd_weight_bias(const void* dy, const void* x, float* dw, float* db, int64_t m, int64_t k,
+                                int64_t n_out, int64_t lddy, int64_t ldx, int64_t lddw, int dtype, void* ws,
+                                size_t ws_bytes, void* stream);
 int gwen_linear_bwd_weight_workspace_bytes(int64_t m, int64_t k, int64_t n_out,
                                            size_t* bytes_out_host);
 
