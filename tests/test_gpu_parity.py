@@ -618,7 +618,7 @@ def test_host_propagator_matches_device_path(dev, chunks):
 # ---------------------------------------------------------------------------------------------
 # training-step glue: fused masked L1 loss, train_step
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(154, 24), (3, 154, 24), (1000, 100), (2, 70, 1)])
+@pytest.mark.parametrize("shape", [(154, 24), (3, 154, 24), (1000, 100), (2, 70, 1), (2, 333, 64)])
 def test_masked_l1_loss_matches_reference_loss_func(dev, shape):
     n = shape[-2]
     y, t = wts.features(shape, 1), wts.features(shape, 2)
@@ -638,6 +638,12 @@ def test_masked_l1_loss_matches_reference_loss_func(dev, shape):
     lb = gw.masked_l1_loss(yb.to(dev), tb.to(dev), mask.to(dev))
     ref_b = (yb.float() - tb.float()).abs()[..., mask, :].mean()
     assert abs(lb.item() - ref_b.item()) <= 1e-5 * abs(ref_b.item())
+    # bf16 gradient (16-byte vector kernel when the width allows, scalar otherwise): sign(y - t) * mask * scale
+    ybd = yb.to(dev).requires_grad_(True)
+    (gw.masked_l1_loss(ybd, tb.to(dev), mask.to(dev)) * 3.0).backward()
+    cnt = int(mask.sum()) * (shape[0] if len(shape) == 3 else 1) * shape[-1]
+    gref = (torch.sign(yb.float() - tb.float()) * mask.view(-1, 1) * (3.0 / cnt)).bfloat16()
+    assert torch.equal(ybd.grad.cpu(), gref)
     # empty mask -> NaN, as the mean of an empty selection
     assert torch.isnan(gw.masked_l1_loss(yd, t.to(dev), torch.zeros(n, dtype=torch.bool, device=dev)))
 
