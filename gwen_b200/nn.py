@@ -40,6 +40,7 @@ class ReluLink:
 
 import os as _os0
 BWD_MASK_FUSION = _os0.environ.get("GWEN_BWD_MASK_FUSION", "1") != "0"
+FUSED_IN_TRAINING = _os0.environ.get("GWEN_FUSED_TRAIN", "0") == "1"
 
 
 class _GCNConvFn(torch.autograd.Function):
@@ -49,7 +50,11 @@ class _GCNConvFn(torch.autograd.Function):
     def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], graph: GraphCSR,
                 relu: bool, agg_first: bool, link_in: Optional[ReluLink] = None,
                 link_out: Optional[ReluLink] = None):
-        fused = agg_first and ops.gcn_fused_preferred(graph, x, weight)
+        # the fused kernel keeps A_hat x on chip -- which the backward needs (dW = dy^T (A_hat x)): in training the
+        # two-kernel form, whose aggregated tensor is saved, beats fused + recomputing the stencil in backward
+        # (measured per member step at the cfg 5 shape); GWEN_FUSED_TRAIN=1 restores the fused forward
+        training = any(ctx.needs_input_grad[:3])
+        fused = agg_first and (FUSED_IN_TRAINING or not training) and ops.gcn_fused_preferred(graph, x, weight)
         if fused:          # (A_hat x) W^T in ONE kernel: the aggregated rows never leave the SM
             y = ops.gcn_fused(graph, x, weight, bias, relu)
             saved_in = x   # backward recomputes A_hat x (one narrow stencil) instead of storing it

@@ -703,7 +703,9 @@ def test_fused_layer_matches_two_kernel_path(dev, hw, k, n, batch):
 
 
 def test_fused_layer_autograd_matches_unfused(dev, monkeypatch):
+    from gwen_b200 import nn as gnn
     monkeypatch.setattr(ops, "FUSED_MIN_ITEMS", 0)        # force the fused choice on a small mesh
+    monkeypatch.setattr(gnn, "FUSED_IN_TRAINING", True)   # ... also when gradients are wanted (default: two kernels)
     h, w, k, n = 21, 19, 64, 256
     g = gw.build_graph(gw.grid(h, w, dev), h * w)
     x = wts.features((2, h * w, k), 41).bfloat16().to(dev)
