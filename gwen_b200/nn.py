@@ -14,6 +14,7 @@ projection is narrower -- with bias and an optional fused ReLU in the last kerne
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -38,9 +39,8 @@ class ReluLink:
         self.masked = False
 
 
-import os as _os0
-BWD_MASK_FUSION = _os0.environ.get("GWEN_BWD_MASK_FUSION", "1") != "0"
-FUSED_IN_TRAINING = _os0.environ.get("GWEN_FUSED_TRAIN", "0") == "1"
+BWD_MASK_FUSION = os.environ.get("GWEN_BWD_MASK_FUSION", "1") != "0"   # fold ReLU masks into the next layer's dgrad
+FUSED_IN_TRAINING = os.environ.get("GWEN_FUSED_TRAIN", "0") == "1"      # fused layer kernel also when gradients are wanted
 
 
 class _GCNConvFn(torch.autograd.Function):
@@ -137,8 +137,7 @@ def gcn_conv(x: Tensor, graph: GraphCSR, weight: Tensor, bias: Optional[Tensor] 
 #     y  = epi_b(q + bb) comes out of the fused kernel's epilogue otherwise.
 # The A operand is rounded to bf16 exactly where the layer-by-layer path stores conv_a's output, so the result
 # is bitwise equal to it.
-import os as _os
-PAIR_FUSION = _os.environ.get("GWEN_PAIR_FUSION", "1") != "0"
+PAIR_FUSION = os.environ.get("GWEN_PAIR_FUSION", "1") != "0"
 
 
 def pair_fusable(graph: GraphCSR, x: Tensor, conv_a: "GCNConv", conv_b: "GCNConv") -> bool:
@@ -172,8 +171,8 @@ def gcn_conv_pair(x: Optional[Tensor], graph: GraphCSR, conv_a: "GCNConv", conv_
 #     p = relu(a Wa^T + ba) Wb^T            (two tcgen05 products back to back)
 # and p, conv_b's un-aggregated projection, goes on to conv_b's aggregation (or into the pair fusion above).
 # The hidden block is rounded to bf16 exactly where the layer-by-layer path stores conv_a's output.
-B2B_FUSION = _os.environ.get("GWEN_B2B_FUSION", "1") != "0"
-B2B_PAIRS = _os.environ.get("GWEN_B2B_PAIRS", "down,up").split(",")   # which pairs may fuse: conv1->conv2 (down), upconv4->upconv5 (up)
+B2B_FUSION = os.environ.get("GWEN_B2B_FUSION", "1") != "0"
+B2B_PAIRS = os.environ.get("GWEN_B2B_PAIRS", "down,up").split(",")   # which pairs may fuse: conv1->conv2 (down), upconv4->upconv5 (up)
 B2B_MIN_ROWS = 500_000     # rows (members x nodes) from which the one kernel beats the two layers' kernels (measured)
 
 

@@ -8,6 +8,7 @@ CPU tensor raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -34,8 +35,7 @@ _DTYPES = {torch.float32: _lib.GWEN_F32, torch.bfloat16: _lib.GWEN_BF16}
 #             locality; bitwise equal to "rows".  "auto" takes it for sparse graphs of >= LOCALITY_MIN_NODES nodes
 #             that are not grid-numbered, and falls back to rows when the graph has no locality
 DEFAULT_AGG_KERNEL = "auto"
-import os as _os
-LOCALITY_TILES = _os.environ.get("GWEN_LOCALITY_TILES", "1") != "0"
+LOCALITY_TILES = os.environ.get("GWEN_LOCALITY_TILES", "1") != "0"
 LOCALITY_MIN_NODES = 32768        # below this the row kernel's working set sits in L2 anyway
 LOCALITY_MAX_DEGREE = 32          # mean messages per destination above which a tile's sources cannot fit
 
