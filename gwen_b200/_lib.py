@@ -111,6 +111,8 @@ PROTOTYPES = {
     "gwen_linear_fwd_ws": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p, _int, _p, _sz, _p]),
     "gwen_linear_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
     "gwen_linear_bwd_data_masked": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int, _p]),
+    "gwen_linear_batched_bwd_data_masked": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,
+                                                   _i64, _i64, _int, _p]),
     "gwen_linear_batched_fwd": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                        _p, _int, _p]),
     "gwen_linear_batched_bwd_data": (_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64,

@@ -36,7 +36,8 @@ int linear_tc_batched_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx
                                 const void* y, int b_mn);
 int linear_tc_batched_bf16(const void* x, const void* w, void* y, int64_t batch, int64_t m, int64_t k,
                            int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int64_t x_bstride,
-                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st);
+                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st,
+                           const void* mask = nullptr, int64_t ldm = 0, int64_t m_bstride = 0);
 // linear_tf32x3.cu
 int linear_tf32x3_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy,
                             const void* x, const void* w, const void* y);
@@ -473,6 +474,22 @@ extern "C" int gwen_linear_bwd_data_masked(const void* dy, const void* weight, v
     return set_err(GWEN_E_NOSUPPORT, "masked dgrad runs on the bf16 tcgen05 pair kernel only");
   return linear_tc_dgrad_bf16(dy, weight, dx, m, k, n_out, lddy, ldw, lddx, static_cast<cudaStream_t>(stream), mask,
                               ldmask);
+}
+
+// The same over `batch` slices in ONE launch (batch-strided dy / dx / mask, e.g. the owned rows of a band buffer)
+extern "C" int gwen_linear_batched_bwd_data_masked(const void* dy, const void* weight, void* dx, const void* mask,
+                                                   int64_t batch, int64_t m, int64_t k, int64_t n_out, int64_t lddy,
+                                                   int64_t ldw, int64_t lddx, int64_t ldmask, int64_t dy_bstride,
+                                                   int64_t dx_bstride, int64_t mask_bstride, int dtype, void* stream) {
+  GWEN_CHECK_ARG(batch >= 1 && m >= 0 && k >= 0 && n_out >= 0, "bad sizes");
+  if (check_dtype(dtype) != GWEN_OK) return GWEN_E_DTYPE;
+  GWEN_CHECK_ARG(dy && weight && dx && mask, "null pointer");
+  GWEN_CHECK_ARG(lddy >= n_out && ldw >= k && lddx >= k && ldmask >= k, "row pitch too small");
+  if (dtype != GWEN_BF16 || m == 0 || k == 0 || ldmask % 8 || mask_bstride % 8 || (reinterpret_cast<uintptr_t>(mask) & 15u) ||
+      !linear_tc_batched_supported(m, n_out, k, lddy, ldw, lddx, dy_bstride, dx_bstride, dy, weight, dx, 1))
+    return set_err(GWEN_E_NOSUPPORT, "masked dgrad runs on the bf16 tcgen05 pair kernel only");
+  return linear_tc_batched_bf16(dy, weight, dx, batch, m, n_out, k, lddy, ldw, lddx, dy_bstride, dx_bstride, nullptr, 0,
+                                1, static_cast<cudaStream_t>(stream), mask, ldmask, mask_bstride);
 }
 
 extern "C" int gwen_linear_batched_fwd(const void* x, const void* weight, void* y, int64_t batch, int64_t m,

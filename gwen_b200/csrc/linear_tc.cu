@@ -431,9 +431,10 @@ int linear_tc_batched_supported(int64_t m, int64_t k, int64_t n_out, int64_t ldx
 }
 int linear_tc_batched_bf16(const void* x, const void* w, void* y, int64_t batch, int64_t m, int64_t k,
                            int64_t n_out, int64_t ldx, int64_t ldw, int64_t ldy, int64_t x_bstride,
-                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st) {
+                           int64_t y_bstride, const float* bias, int relu, int b_mn, cudaStream_t st,
+                           const void* mask, int64_t ldm, int64_t m_bstride) {
   return linear_tc3_fwd_bf16(x, w, y, m, k, n_out, ldx, ldw, ldy, bias, relu, b_mn, st, batch, x_bstride,
-                             y_bstride);
+                             y_bstride, mask, ldm, m_bstride);
 }
 
 }  // namespace gwen

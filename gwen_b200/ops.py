@@ -419,7 +419,8 @@ def linear_bwd_data(dy: torch.Tensor, weight: torch.Tensor, out: Optional[torch.
     return dx.reshape(tuple(dy.shape[:-1]) + (k,))
 
 
-def linear_bwd_data_masked(dy: torch.Tensor, weight: torch.Tensor, mask: torch.Tensor) -> Optional[torch.Tensor]:
+def linear_bwd_data_masked(dy: torch.Tensor, weight: torch.Tensor, mask: torch.Tensor,
+                           out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """``(dy @ weight) * (mask > 0)`` in ONE kernel (``gwen_linear_bwd_data_masked``: the previous layer's ReLU
     backward in the dgrad epilogue), ``mask`` = the layer input (bf16, shape of the result).  Returns None when the
     fused kernel does not serve the problem (not bf16, shapes outside the tcgen05 pair kernel): the caller then runs
@@ -427,6 +428,22 @@ def linear_bwd_data_masked(dy: torch.Tensor, weight: torch.Tensor, mask: torch.T
     n_out, k = weight.shape
     if dy.dtype != torch.bfloat16 or mask.dtype != torch.bfloat16 or mask.shape[-1] != k:
         return None
+    if out is not None:   # batch-strided destination (dense rows), e.g. the owned rows of a band buffer: one launch
+        dv, mv, ov = _rows_view(dy if dy.is_contiguous() else dy.contiguous()), _rows_view(mask), _rows_view(out)
+        if dv is None or mv is None or ov is None or out.dtype != dy.dtype or ov.shape[2] != k or \
+                not (dv.shape[:2] == mv.shape[:2] == ov.shape[:2]):
+            return None
+        wt = _cast_cached(weight, dy.dtype)
+        nb = dv.shape[0]
+        with torch.cuda.device(dy.device):
+            rc = lib().gwen_linear_batched_bwd_data_masked(
+                _ptr(dv), _ptr(wt), _ptr(ov), _ptr(mv), nb, dv.shape[1], k, n_out, n_out, k, k, k,
+                dv.stride(0) if nb > 1 else 0, ov.stride(0) if nb > 1 else 0, mv.stride(0) if nb > 1 else 0,
+                dtype_code(dy.dtype), _stream())
+        if rc == _lib.GWEN_E_NOSUPPORT:
+            return None
+        check(rc, "gwen_linear_batched_bwd_data_masked")
+        return out
     dy2 = dy.reshape(-1, n_out).contiguous()
     m2 = mask.reshape(-1, k)
     if m2.shape[0] != dy2.shape[0] or not m2.is_contiguous():

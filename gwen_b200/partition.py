@@ -485,7 +485,10 @@ class _BandGCNFn(torch.autograd.Function):
                 dx = band.aggregate(gs)
             else:
                 if li > 0 and net.layers[li - 1][1] and _nn.BWD_MASK_FUSION:   # x = relu(layer li - 1): its mask here
-                    dx = ops.linear_bwd_data_masked(dh, weight, saved_in)
+                    dst = None
+                    if not net._agg_first[li - 1]:    # that layer aggregates its gradient: write it where it is staged
+                        dst = band.owned(net.buffer(("b", li - 1), b, weight.shape[1], dh.dtype))
+                    dx = ops.linear_bwd_data_masked(dh, weight, saved_in, out=dst)
                     if dx is not None:
                         net._masked[li - 1] = True
                 if dx is None:

@@ -330,6 +330,11 @@ int gwen_linear_bwd_data(const void* dy, const void* weight, void* dx, int64_t m
 int gwen_linear_bwd_data_masked(const void* dy, const void* weight, void* dx, const void* mask, int64_t m, int64_t k,
                                 int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx, int64_t ldmask, int dtype,
                                 void* stream);
+/* ... over `batch` slices in one launch (batch-strided dy / dx / mask: e.g. dx = the owned rows of a band buffer). */
+int gwen_linear_batched_bwd_data_masked(const void* dy, const void* weight, void* dx, const void* mask, int64_t batch,
+                                        int64_t m, int64_t k, int64_t n_out, int64_t lddy, int64_t ldw, int64_t lddx,
+                                        int64_t ldmask, int64_t dy_bstride, int64_t dx_bstride, int64_t mask_bstride,
+                                        int dtype, void* stream);
 /* Batched forms: `batch` independent row blocks x[b] = x + b * x_bstride ([m, k], row pitch ldx) against the
  * SAME weight, results to y[b] = y + b * y_bstride -- e.g. the owned rows of a band buffer per ensemble
  * member.  bf16 problems the CTA-pair kernel takes run as ONE launch (the batch index is the third TMA
