@@ -509,7 +509,9 @@ def probe_strong_cfg4(dev, world, rank):
     ms_t = _timed_dist(train, 2, 3, dev)
     res = {"workload": "cfg4: 2048x2048 mesh (4194304 nodes), six layers, bf16, B=1, FIXED global size (strong scaling), "
                        "row bands over %d GPUs, halo rows pulled over NVLink inside the aggregation kernels, weight "
-                       "gradients all-reduced per layer under the remaining backward" % world,
+                       "gradients written into one flat fp32 buffer during backward and all-reduced in place (%s)" % (
+                           world, "one NCCL call after backward" if os.environ.get("GWEN_GRAD_BUCKETS", "flat") != "layer"
+                           else "per layer, under the remaining backward"),
            "n_gpus": world, "fwd_ms": ms_f, "fwd_bwd_allreduce_ms": ms_t, "step_launch": "eager launches",
            "peer_error_word": band.error_word()}
     # the same step replayed from a CUDA graph (no host launch latency between the ~100 short kernels)

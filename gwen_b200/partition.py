@@ -27,6 +27,8 @@ from typing import List, Optional, Sequence
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -455,8 +457,11 @@ class _BandGCNFn(torch.autograd.Function):
         dx = None
         # weight gradient: written straight into this layer's slice of the flat fp32 gradient buffer and
         # all-reduced from there while the remaining layers' backward runs (net.overlap_grads)
-        if net.overlap_grads and li in net._pending:
-            net._deliver(li)            # an earlier backward's bucket is still in flight: deliver it first
+        if net.overlap_grads and li in net._pending:   # an earlier backward's bucket is still pending: deliver it first
+            if net.bucket_mode == "layer":
+                net._deliver(li)
+            else:
+                net.allreduce_grads()
         wv = net.grad_views(li)[0] if net.overlap_grads else None
         if ctx.agg_first:
             dw = None
@@ -504,15 +509,21 @@ class BandGNNModel(torch.nn.Module):
     sums over their own rows).  Outputs are bitwise equal to the un-partitioned model's rows.
 
     ``overlap_grads`` (default): every layer's backward writes its fp32 ``dW`` / ``db`` into that layer's
-    slice of ONE pre-flattened gradient buffer and starts the NCCL all-reduce of the slice at once, so the
-    reductions of the late layers run under the backward of the early ones; ``allreduce_grads`` then only
-    waits for the handles and hands the (summed) slices to ``p.grad`` -- no ``torch.cat``, no copy-back.
+    slice of ONE pre-flattened gradient buffer; ``allreduce_grads`` reduces the buffer in place with one NCCL
+    all-reduce and hands the (summed) slices to ``p.grad`` -- no ``torch.cat``, no copy-back.  With
+    ``GWEN_GRAD_BUCKETS=layer`` each slice's all-reduce starts inside that layer's backward instead and runs under
+    the backward of the earlier layers (``allreduce_grads`` then only waits for the handles).
     With ``overlap_grads=False`` autograd delivers the local gradients and ``allreduce_grads`` reduces
     them in one flat all-reduce afterwards."""
 
     def __init__(self, model, band: "PeerMeshBand", overlap_grads: bool = True):
         super().__init__()
         self.model, self.band, self.overlap_grads = model, band, overlap_grads
+        # "flat" (default): ONE in-place all-reduce of the flat gradient buffer after backward -- nothing shares the SMs
+        # with the persistent kernels meanwhile; "layer": a bucket's all-reduce starts inside that layer's backward and
+        # runs under the remaining layers (measured: the NCCL kernels then take SMs from the 148-CTA kernels beside
+        # them -- cfg 5 shape, 21 members at N = 2: 138.5 ms vs 132.6-133.9 flat; N = 8: cfg 4 8.05 vs 7.77 ms)
+        self.bucket_mode = os.environ.get("GWEN_GRAD_BUCKETS", "flat")
         self._flat = None
         self._views = {}
         self._pending = {}
@@ -592,14 +603,18 @@ class BandGNNModel(torch.nn.Module):
                 bv.copy_(db)
             else:
                 bv.zero_()
-        self._pending[li] = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.band.group, async_op=True)
+        if self.bucket_mode == "layer":
+            self._pending[li] = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=self.band.group, async_op=True)
+        else:               # "flat": one all-reduce of the whole flat buffer in allreduce_grads()
+            self._pending[li] = None
 
     def _deliver(self, li: int) -> None:
         """Wait for layer ``li``'s bucket and add it to the parameters' ``.grad``."""
-        work = self._pending.pop(li, None)
-        if work is None:
+        if li not in self._pending:
             return
-        work.wait()
+        work = self._pending.pop(li)
+        if work is not None:
+            work.wait()
         conv = self.layers[li][0]
         wv, bv, _ = self._views[li]
         for p, v in ((conv.lin.weight, wv), (conv.bias, bv)):
@@ -613,6 +628,8 @@ class BandGNNModel(torch.nn.Module):
         all-reduces were started inside backward; wait for them and deliver the slices.  Otherwise: one
         flat NCCL all-reduce of the local gradients autograd delivered."""
         if self.overlap_grads:
+            if self.bucket_mode != "layer" and self._pending:
+                dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.band.group)
             for li in sorted(self._pending, reverse=True):   # completion order: last layer first
                 self._deliver(li)
             return
