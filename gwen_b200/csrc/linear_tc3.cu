@@ -68,7 +68,8 @@ __device__ __forceinline__ uint32_t gt0_mask(uint32_t y2) {
 // the staging buffer the output will be packed into, one chunk ahead (two staging buffers per warp); each thread
 // reads back the 64 bytes of its row, ANDs its packed bf16 pairs with the compare mask and overwrites them.
 // Measured (512->1024 dgrad, M = 896 292, plain kernel 751 us): this form with an integer compare per half 1105 us;
-// + the operand producer prefetching the next tile's mask block into L2 (UTMAPF) 1145 us; per-thread 16-byte
+// + the operand producer prefetching the next tile's mask block into L2 (UTMAPF) 1145 us (and, with the HSET2 compare,
+// the epilogue warp prefetching its chunk-after-next tile: 980 -> 1000 us: the mask's latency is not the bound); per-thread 16-byte
 // read-only loads of the mask row instead of the TMA tile 1164 us.
 template <bool kMask>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTc3Threads, 1)
