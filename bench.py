@@ -703,6 +703,12 @@ def run_ours(args):
 
     def timed_region(k):
         sync_all()
+        if world > 1:
+            # the ranks leave the barrier up to ~1 ms apart, and a partitioned step cannot finish before its
+            # neighbours have started theirs: without this the first timed step absorbs that skew (a 20-step region
+            # is 1.7 ms).  One more UNTIMED step lines the ranks up on the device (each waits for its neighbours'
+            # epoch flags); the start event is recorded behind it on the stream.
+            steps_fn[NBUF - 1]()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(k):
@@ -871,6 +877,10 @@ def run_ours(args):
                        "l2": "the step rotates over %d input/output buffer pairs (%.0f MB per rank > 126 MB L2): no line survives "
                              "in L2 between two uses of a buffer, no explicit flush" % (NBUF, NBUF * 2 * n_own * FEAT * 4 / 1e6),
                        "step_launch": step_mode,
+                       "timing": "CUDA events on the launching stream around exactly K steps, max over ranks, barrier + "
+                                 "synchronize on both sides" + ("; at N > 1 one untimed step behind the opening barrier "
+                                 "lines the ranks up on the device, so the region does not include the barrier's exit skew"
+                                 if world > 1 else ""),
                        "kernel": "k_grid_stencil (mesh fast path: 8x16 tiles, one 4-D TMA box per tile/slab, "
                                  "separable column sums in packed fp32x2 registers); exact CSR kernels "
                                  "k_agg_tiled / k_agg_rows remain for arbitrary graphs"},
